@@ -1,0 +1,384 @@
+// TMA-fed tcgen05 implicit-GEMM convolution (3x3 "same" or 1x1, stride 1) for sm_100a.
+//
+// Replaces the cuDNN fp16 Conv2d/Conv1d calls made by the reference U-Net
+// (models/DDNM/guided_diffusion/unet.py:176-222 ResBlock convs, :291-294 attention qkv/proj,
+//  fp16 torso per unet.py:619-625 / fp16_util.py:15-22).
+//
+// GEMM view:  D[M = B*H*W, N = Cout] = A[M, K = taps*Cin] * Wt[N, K]^T  (+bias, +residual)
+//   * activations are NHWC fp16; the A operand of every (tap, 64-channel chunk) is ONE 4-D TMA box
+//     {64 ch, bw, bh, bb} (bw*bh*bb = 128 output pixels) whose (x, y) coordinates are shifted by
+//     the tap offset: TMA zero-fills out-of-bounds elements, which IS the conv's zero padding,
+//     so no im2col buffer ever exists;
+//   * weights are [Cout][taps*Cin] fp16 (K contiguous), one 2-D TMA box {64, BN} per chunk;
+//   * both land in shared memory in the 128-byte-swizzled K-major layout tcgen05.mma consumes;
+//   * accumulators live in TMEM (2 x BN fp32 columns, double buffered) so the epilogue of tile i
+//     overlaps the MMAs of tile i+1;  persistent CTAs (one per SM) walk the tile list.
+//   * A may come from TWO tensors (channel concat of the decoder's skip connection,
+//     unet.py:660-662) so the concat is never materialised.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..7 = epilogue (TMEM -> registers -> +bias (+residual) -> fp16 -> global).
+#include <cuda.h>
+#include "common.cuh"
+#include "conv_tc.h"
+
+namespace pdr {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;  // 64 fp16 = 128 B = one swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int NUM_THREADS = 256;
+
+struct ConvArgs {
+  int B, H, W;
+  int C1, C2;  // channels of the two A sources (C2 may be 0)
+  int Cout;
+  int taps;  // 9 (3x3, pad 1) or 1 (1x1)
+  int bw, bh, bb;
+  int tiles_x, tiles_y, tiles_b, tiles_n;
+  const float* bias;        // [Cout] or null
+  const __half* residual;   // [B,H,W,Cout] or null
+  __half* out;              // [B,H,W,Cout]
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const ConvArgs args) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16-B aligned by the ABI: realign to 1024 B for SWIZZLE_128B
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  uint64_t* full_bar = (uint64_t*)(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int Ctot = args.C1 + args.C2;
+  const int kchunks_per_tap = Ctot / BLOCK_K;
+  const int num_k = args.taps * kchunks_per_tap;
+  const int tiles_m = args.tiles_b * args.tiles_y * args.tiles_x;
+  const int num_tiles = tiles_m * args.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    if (args.C2 > 0) tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer ====
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % args.tiles_n;
+        int m_tile = tile / args.tiles_n;
+        const int tx = m_tile % args.tiles_x;
+        m_tile /= args.tiles_x;
+        const int ty = m_tile % args.tiles_y;
+        const int tb = m_tile / args.tiles_y;
+        const int x0 = tx * args.bw, y0 = ty * args.bh, b0 = tb * args.bb;
+        const int n0 = n_tile * BN;
+        for (int k = 0; k < num_k; ++k) {
+          const int tap = k / kchunks_per_tap;
+          const int kc = k - tap * kchunks_per_tap;
+          int dy = 0, dx = 0;
+          if (args.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          const int c = kc * BLOCK_K;
+          if (c < args.C1)
+            tma_load_4d(sa, &tmA1, &full_bar[stage], c, x0 + dx, y0 + dy, b0);
+          else
+            tma_load_4d(sa, &tmA2, &full_bar[stage], c - args.C1, x0 + dx, y0 + dy, b0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ======================================================= MMA issuer ====
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_f16(BLOCK_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int k = 0; k < num_k; ++k) {
+          mbar_wait(&full_bar[stage], phase);  // TMA bytes landed
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + kk * UMMA_K * 2);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + kk * UMMA_K * 2);
+            umma_f16(tmem_d, adesc, bdesc, idesc, (k | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ========================================================= epilogue ====
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;  // row of the tile == TMEM lane
+    const int pw = r % args.bw;
+    const int ph = (r / args.bw) % args.bh;
+    const int pb = r / (args.bw * args.bh);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_tile = tile % args.tiles_n;
+      int m_tile = tile / args.tiles_n;
+      const int tx = m_tile % args.tiles_x;
+      m_tile /= args.tiles_x;
+      const int ty = m_tile % args.tiles_y;
+      const int tb = m_tile / args.tiles_y;
+      const int x = tx * args.bw + pw, y = ty * args.bh + ph, b = tb * args.bb + pb;
+      const int n0 = n_tile * BN;
+      const bool valid = (b < args.B) && (y < args.H) && (x < args.W);
+      const size_t row_off = (((size_t)b * args.H + y) * args.W + x) * (size_t)args.Cout + n0;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          const int nb = n0 + ch * 32;
+          __align__(16) __half o[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (args.bias) bv = __ldg((const float4*)(args.bias + nb + j));
+            o[j + 0] = __float2half_rn(__uint_as_float(v[j + 0]) + bv.x);
+            o[j + 1] = __float2half_rn(__uint_as_float(v[j + 1]) + bv.y);
+            o[j + 2] = __float2half_rn(__uint_as_float(v[j + 2]) + bv.z);
+            o[j + 3] = __float2half_rn(__uint_as_float(v[j + 3]) + bv.w);
+          }
+          if (args.residual) {
+            // reference adds two fp16 tensors (unet.py:256, :305): fp32 add, one more rounding
+            const uint4* rp = (const uint4*)(args.residual + row_off + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 rv = __ldg(rp + j);
+              const __half* rh = (const __half*)&rv;
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                o[j * 8 + e] =
+                    __float2half_rn(__half2float(o[j * 8 + e]) + __half2float(rh[e]));
+            }
+          }
+          uint4* op = (uint4*)(args.out + row_off + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = ((const uint4*)o)[j];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// ------------------------------------------------------------------ host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  // resolved through the runtime so the library has no link-time dependency on libcuda
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+void conv_tc_pick_box(int B, int H, int W, int* bw, int* bh, int* bb) {
+  int w = W < 16 ? W : 16;
+  int h = 128 / w;
+  if (h > H) h = H;
+  int b = 128 / (w * h);
+  *bw = w;
+  *bh = h;
+  *bb = b;
+  (void)B;
+}
+
+int conv_tc_make_act_map(ConvTensorMap* out, const void* ptr, int B, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode_fn();
+  PDR_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  PDR_CHECK_ARG(C % BLOCK_K == 0, "activation channels (%d) must be a multiple of 64", C);
+  PDR_CHECK_ARG(((uintptr_t)ptr & 15) == 0, "activation pointer must be 16-byte aligned");
+  int bw, bh, bb;
+  conv_tc_pick_box(B, H, W, &bw, &bh, &bb);
+  PDR_CHECK_ARG(bw * bh * bb == 128 && W % bw == 0 && H % bh == 0,
+                "unsupported spatial size %dx%d for the 128-pixel tile", H, W);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)ptr, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PDR_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(act) failed: CUresult %d", (int)r);
+  return 0;
+}
+
+int conv_tc_make_weight_map(ConvTensorMap* out, const void* ptr, int Cout, int K, int BN) {
+  EncodeTiledFn enc = get_encode_fn();
+  PDR_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  PDR_CHECK_ARG(K % BLOCK_K == 0 && Cout % BN == 0, "weight shape [%d,%d] not tileable by %d",
+                Cout, K, BN);
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PDR_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: CUresult %d", (int)r);
+  return 0;
+}
+
+int conv_tc_pick_bn(int B, int H, int W, int Cout) {
+  // BN = 256 halves A re-reads; fall back to 128 when that leaves SMs idle.
+  if (Cout % 256 != 0) return 128;
+  int bw, bh, bb;
+  conv_tc_pick_box(B, H, W, &bw, &bh, &bb);
+  long long tiles_m = (long long)cdiv(B, bb) * (H / bh) * (W / bw);
+  if (tiles_m * (Cout / 256) < num_sms()) return 128;
+  return 256;
+}
+
+template <int BN, int STAGES>
+static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
+                       const ConvArgs& args, cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  constexpr int smem_bytes = L::TOTAL + 1024;  // +1024 for the manual realignment
+  static bool configured = false;
+  if (!configured) {
+    PDR_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  const int tiles = args.tiles_b * args.tiles_y * args.tiles_x * args.tiles_n;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem_bytes, stream>>>(
+      *(const CUtensorMap*)a1, *(const CUtensorMap*)(a2 ? a2 : a1), *(const CUtensorMap*)w, args);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
+                   int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
+                   const float* bias, const __half* residual, __half* out, cudaStream_t stream) {
+  PDR_CHECK_ARG(taps == 9 || taps == 1, "taps must be 9 or 1 (got %d)", taps);
+  PDR_CHECK_ARG(C1 > 0 && C1 % BLOCK_K == 0 && C2 % BLOCK_K == 0, "C1/C2 must be multiples of 64");
+  PDR_CHECK_ARG(BN == 128 || BN == 256, "BN must be 128 or 256");
+  PDR_CHECK_ARG(Cout % BN == 0, "Cout (%d) must be a multiple of BN (%d)", Cout, BN);
+  PDR_CHECK_ARG(C2 == 0 || a2 != nullptr, "second A tensor map missing");
+  ConvArgs args;
+  args.B = B;
+  args.H = H;
+  args.W = W;
+  args.C1 = C1;
+  args.C2 = C2;
+  args.Cout = Cout;
+  args.taps = taps;
+  conv_tc_pick_box(B, H, W, &args.bw, &args.bh, &args.bb);
+  PDR_CHECK_ARG(args.bw * args.bh * args.bb == 128 && W % args.bw == 0 && H % args.bh == 0,
+                "unsupported spatial size %dx%d", H, W);
+  args.tiles_x = W / args.bw;
+  args.tiles_y = H / args.bh;
+  args.tiles_b = cdiv(B, args.bb);
+  args.tiles_n = Cout / BN;
+  args.bias = bias;
+  args.residual = residual;
+  args.out = out;
+  if (BN == 256) return launch_impl<256, 4>(a1, a2, w, args, stream);
+  return launch_impl<128, 6>(a1, a2, w, args, stream);
+}
+
+}  // namespace pdr

@@ -1,0 +1,29 @@
+// Host interface of the tcgen05 implicit-GEMM convolution (conv_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace pdr {
+
+// opaque CUtensorMap (128 bytes, 64-byte aligned)
+struct alignas(64) ConvTensorMap {
+  uint8_t bytes[128];
+};
+
+// 128-output-pixel tile of an H x W feature map: bw*bh*bb == 128
+void conv_tc_pick_box(int B, int H, int W, int* bw, int* bh, int* bb);
+// N tile (128 or 256) that keeps all SMs busy for this layer
+int conv_tc_pick_bn(int B, int H, int W, int Cout);
+
+// NHWC fp16 activation [B,H,W,C], C % 64 == 0
+int conv_tc_make_act_map(ConvTensorMap* out, const void* ptr, int B, int H, int W, int C);
+// fp16 weights [Cout][K] with K = taps*Cin ordered (tap, channel)
+int conv_tc_make_weight_map(ConvTensorMap* out, const void* ptr, int Cout, int K, int BN);
+
+// out[B,H,W,Cout] = conv(cat(A1,A2)) + bias (+ residual); taps = 9 (3x3 pad 1) or 1 (1x1)
+int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
+                   int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
+                   const float* bias, const __half* residual, __half* out, cudaStream_t stream);
+
+}  // namespace pdr

@@ -1,0 +1,71 @@
+"""tcgen05 implicit-GEMM conv vs a plain PyTorch fp32 reference of the same op (GPU)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from pointdreamer_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cuda, B, H, W, C1, C2, Cout, taps, bn, bias=True, residual=False, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x1 = (torch.randn(B, H, W, C1, generator=g)).half().to(cuda)
+    x2 = (torch.randn(B, H, W, C2, generator=g)).half().to(cuda) if C2 else None
+    k = 3 if taps == 9 else 1
+    C = C1 + C2
+    w = (torch.randn(Cout, C, k, k, generator=g) / (C * k * k) ** 0.5).half().to(cuda)
+    b = torch.randn(Cout, generator=g).to(cuda) if bias else None
+    res = torch.randn(B, H, W, Cout, generator=g).half().to(cuda) if residual else None
+    out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=cuda)
+    # [Cout][tap][C]
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, taps * C).contiguous()
+    _lib.call("pdr_conv_tc", _lib.ptr(x1), _lib.ptr(x2), _lib.ptr(wk), _lib.ptr(b), _lib.ptr(res),
+              _lib.ptr(out), B, H, W, C1, C2, Cout, taps, bn)
+    torch.cuda.synchronize()
+    xin = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = F.conv2d(xin.float().permute(0, 3, 1, 2), w.float(), b, padding=k // 2)
+    ref = ref.half()  # reference rounds the conv output to fp16 ...
+    if residual:
+        ref = (ref.float() + res.float().permute(0, 3, 1, 2)).half()  # ... then adds in fp16
+    ref = ref.permute(0, 2, 3, 1).float()
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"conv B{B} {H}x{W} C{C1}+{C2}->{Cout} taps{taps} bn{bn}: max_abs_err={err:.3e} "
+          f"ref_max={scale:.3f}")
+    return err, scale
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("taps", [1, 9])
+def test_conv_basic(cuda, bn, taps):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    err, scale = _run(cuda, 2, 16, 16, 64, 0, 256, taps, bn)
+    assert err <= 4e-3 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("shape", [
+    (1, 8, 8, 128, 0, 256, 9),      # bb=2 > B: batch rows out of bounds
+    (3, 8, 8, 64, 64, 128, 9),      # two sources, odd batch
+    (2, 32, 32, 128, 64, 256, 9),   # multi-tile spatial, two sources
+    (1, 64, 64, 256, 0, 256, 9),    # full 256->256 layer shape
+    (2, 16, 16, 192, 0, 384, 1),    # qkv-like 1x1
+    (8, 4, 4, 64, 0, 128, 9),       # tiny image, bb=8
+])
+def test_conv_shapes(cuda, shape):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W, C1, C2, Cout, taps = shape
+    err, scale = _run(cuda, B, H, W, C1, C2, Cout, taps, 0, residual=True)
+    assert err <= 4e-3 * max(scale, 1.0)
+
+
+def test_conv_many_tiles_persistent(cuda):
+    """More tiles than SMs: exercises the persistent loop, TMEM double buffering, ring wrap."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    err, scale = _run(cuda, 4, 128, 128, 64, 0, 256, 9, 256)
+    assert err <= 4e-3 * max(scale, 1.0)
+    err, scale = _run(cuda, 2, 128, 128, 128, 0, 128, 9, 128)
+    assert err <= 4e-3 * max(scale, 1.0)
