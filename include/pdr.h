@@ -43,6 +43,87 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
                 const void* residual, void* out, int B, int H, int W, int C1, int C2, int Cout,
                 int taps, int bn, void* stream);
 
+/* --------------------------------------------------------------- PROJECT --------------- */
+/* Camera transform + crop/rescale of mesh vertices and cloud points for all V views.
+ * Replaces ours_utils.py:93-130 (get_rendered_hard_mask_and_face_idx_batch up to the
+ * rasterize call) incl. kaolin Camera.transform (ours_utils.py:99; canonical arithmetic in
+ * oracle/camera.py).
+ *   cam_params [V,16] fp32 (r00..r22, t0..t2, f, za, zb, 0); vertices [Vm,3]; points [N,3]
+ *   ws_minmax: int[4*V] scratch
+ *   pos [V,Vm,4] (rescaled NDC xy, NDC z, 1) ; vertice_uvs [V,Vm,2] ; uv_centers [V,2] ;
+ *   uv_scales [V] ; point_uvs [V,N,2] ; point_depths [V,N]                     (all fp32) */
+int pdr_project(const float* cam_params, const float* vertices, int Vm, const float* points,
+                int N, int V, int rescale, double padding, int* ws_minmax, float* pos,
+                float* vertice_uvs, float* uv_centers, float* uv_scales, float* point_uvs,
+                float* point_depths, void* stream);
+
+/* Z-buffer rasteriser of the mesh for all views.  Replaces nvdiffrast.torch.rasterize as
+ * used at ours_utils.py:142-147 plus the 512->256 mask resize of demo.py:103-104.
+ *   pos [V,Vm,4] fp32 ; faces [F,3] int32 ; ws_keys: uint64[V*res*res] scratch
+ *   depth [V,res,res] fp32 (0 empty) ; face_idx [V,res,res] int64 (-1 empty) ;
+ *   mask_cam [V,res,res] u8 ; mask_out [V,out_res,out_res] u8 (out_res == res or res/2) */
+int pdr_rasterize(const float* pos, const int* faces, int V, int Vm, int F, int res, int out_res,
+                  unsigned long long* ws_keys, float* depth, long long* face_idx,
+                  uint8_t* mask_cam, uint8_t* mask_out, void* stream);
+
+/* 2x mask reduction.  Replaces demo.py:103-104 (torchvision Resize, bilinear without antialias,
+ * then .bool()  ==  OR of each 2x2 block).  mask_in [V,res_in,res_in] u8 -> [V,res_in/2,res_in/2] */
+int pdr_mask_half_any(const uint8_t* mask_in, int V, int res_in, uint8_t* mask_out, void* stream);
+
+/* Depth visibility + pixel quantisation.  Replaces ours_utils.py:153-202
+ * (get_point_validation_by_depth) and demo.py:121-125 (point_pixels at `res`).
+ * Any of vis / pix_cam / pix_res may be NULL.
+ *   point_uvs [V,N,2] ; point_depths [V,N] ; mesh_depths [V,cam_res,cam_res]
+ *   vis [V,N] u8 ; pix_cam [V,N,2] int64 (row,col at cam_res) ; pix_res [V,N,2] int64 */
+int pdr_point_visibility(const float* point_uvs, const float* point_depths,
+                         const float* mesh_depths, int V, int N, int cam_res, float offset,
+                         int res, uint8_t* vis, long long* pix_cam, long long* pix_res,
+                         void* stream);
+
+/* Sparse view images + hole masks.  Replaces ours_utils.py:848-882 get_sparse_images
+ * (get_one_sparse_img 954-1044, paint_pixels 456-495, inner edge mask 497-532, kaolin
+ * sided_distance 1013).
+ *   point_pixels [V,N,2] int64 (row,col) ; colors [N,3] fp32 ; valid [V,N] u8 ;
+ *   hard_masks [V,res,res] u8 ; workspace: pdr_sparse_images_workspace_bytes(V,res) bytes
+ *   sparse / hard_mask0 / hard_mask2 [V,3,res,res] fp32 ; scale_factors [V] fp32 */
+size_t pdr_sparse_images_workspace_bytes(int V, int res);
+int pdr_sparse_images(const long long* point_pixels, const float* colors, const uint8_t* valid,
+                      const uint8_t* hard_masks, int V, int N, int res, int point_size,
+                      int edge_point_size, double mask_ratio_thresh, void* workspace,
+                      float* sparse, float* hard_mask0, float* hard_mask2, float* scale_factors,
+                      void* stream);
+
+/* Exact nearest-valid-pixel fill.  Replaces ours_utils.py:610-643 naive_inpainting('nearest')
+ * (scipy griddata) and unproject.py:480-504 dilate_atlas.
+ *   img [B,C,H,W] fp32 (channels_last=0) or [B,H,W,C] (channels_last=1) ; known [B,H,W] u8 ;
+ *   out same layout as img ; src_index [B,H,W] int32 (linear index of the source) or NULL */
+size_t pdr_nearest_fill_workspace_bytes(int B, int H, int W);
+int pdr_nearest_fill(const float* img, const uint8_t* known, int B, int C, int H, int W,
+                     int channels_last, void* workspace, float* out, int* src_index,
+                     void* stream);
+
+/* ------------------------------------------------------------- UNPROJECT --------------- */
+/* Back-projection of the inpainted views into the UV atlas with Non-Border-First selection.
+ * Replaces unproject.py:201-425 (unproject), :429-475 (NBF shrink), utils_2d.py:799-845.
+ *   images [V,3,res,res] fp32 ; cam_params [V,16] ; base_dirs [V,3] ; gb_pos [R,R,3] ;
+ *   mask [R,R] u8 ; face_id [R,R] int64 ; f_normals [F,3] ; uv_centers [V,2] ; uv_scales [V] ;
+ *   scale_factors [V] ; mesh_depths [V,cam_res,cam_res] ;
+ *   kernels_host: HOST int[n_levels] = edge_dilate_kernels ; rescale = 0 only when the
+ *   reference's uv_centers/uv_scales/padding/scale_factors would be None (unproject.py:260)
+ *   atlas [R,R,3] fp32 ; shrinked_vis [V,R,R] u8 ; point_view_ids [P] int64 ;
+ *   point_coords [P,2] int64 ; points [P,3] fp32 ; painted [R,R] u8  (P = count of mask) */
+size_t pdr_unproject_workspace_bytes(int R, int n_levels);
+int pdr_unproject(const float* images, int res, const float* cam_params, int V, int cam_res,
+                  const float* base_dirs, const float* gb_pos, const uint8_t* mask,
+                  const long long* face_id, int R, const float* f_normals, int F,
+                  const float* uv_centers, const float* uv_scales, double padding, int rescale,
+                  const float* scale_factors, const float* mesh_depths, const int* kernels_host,
+                  int n_levels, int complete_unseen, void* workspace, float* atlas,
+                  uint8_t* shrinked_vis, long long* point_view_ids, long long* point_coords,
+                  float* points, uint8_t* painted, void* stream);
+/* number of set bytes in mask[n]; synchronises `stream`. ws_counter: int[1] device scratch */
+int pdr_mask_count(const uint8_t* mask, size_t n, int* ws_counter, int* out_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

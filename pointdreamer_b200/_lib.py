@@ -65,12 +65,22 @@ def launch_count():
 
 
 def call(name, *args):
-    """Call `name(*args, stream)` on the current torch CUDA stream and raise on failure."""
+    """Call `name(*args, stream)` on the current torch CUDA stream and raise on failure.
+
+    Tensors may be passed directly (converted to their data pointer here, so temporaries stay
+    alive until the launch is enqueued); None becomes a NULL pointer; Python ints/bools map to
+    C int, Python floats to C float — pass ctypes.c_double / c_size_t / ... explicitly otherwise.
+    """
+    import torch
     lib = load()
     fn = getattr(lib, name)
     conv = []
     for a in args:
-        if isinstance(a, float):
+        if a is None:
+            conv.append(ctypes.c_void_p(0))
+        elif isinstance(a, torch.Tensor):
+            conv.append(ptr(a))
+        elif isinstance(a, float):
             conv.append(ctypes.c_float(a))
         elif isinstance(a, bool):
             conv.append(ctypes.c_int(int(a)))

@@ -2,6 +2,7 @@
 #include "pdr.h"
 #include "common.cuh"
 #include "conv_tc.h"
+#include "geom.h"
 
 using namespace pdr;
 
@@ -27,6 +28,95 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
   PDR_TRY(conv_tc_make_weight_map(&mw, w, Cout, taps * (C1 + C2), bn));
   return conv_tc_launch(&ma1, C2 > 0 ? &ma2 : nullptr, &mw, bn, B, H, W, C1, C2, Cout, taps, bias,
                         (const __half*)residual, (__half*)out, (cudaStream_t)stream);
+}
+
+int pdr_project(const float* cam_params, const float* vertices, int Vm, const float* points,
+                int N, int V, int rescale, double padding, int* ws_minmax, float* pos,
+                float* vertice_uvs, float* uv_centers, float* uv_scales, float* point_uvs,
+                float* point_depths, void* stream) {
+  PDR_CHECK_ARG(cam_params && vertices && points && ws_minmax && pos && vertice_uvs &&
+                    uv_centers && uv_scales && point_uvs && point_depths,
+                "pdr_project: null pointer");
+  return project_launch(cam_params, vertices, Vm, points, N, V, rescale, padding, ws_minmax, pos,
+                        vertice_uvs, uv_centers, uv_scales, point_uvs, point_depths,
+                        (cudaStream_t)stream);
+}
+
+int pdr_rasterize(const float* pos, const int* faces, int V, int Vm, int F, int res, int out_res,
+                  unsigned long long* ws_keys, float* depth, long long* face_idx,
+                  uint8_t* mask_cam, uint8_t* mask_out, void* stream) {
+  PDR_CHECK_ARG(pos && faces && ws_keys && depth && face_idx && mask_cam && mask_out,
+                "pdr_rasterize: null pointer");
+  return rasterize_launch(pos, faces, V, Vm, F, res, out_res, ws_keys, depth, face_idx, mask_cam,
+                          mask_out, (cudaStream_t)stream);
+}
+
+int pdr_mask_half_any(const uint8_t* mask_in, int V, int res_in, uint8_t* mask_out, void* stream) {
+  PDR_CHECK_ARG(mask_in && mask_out, "pdr_mask_half_any: null pointer");
+  return mask_half_any_launch(mask_in, V, res_in, mask_out, (cudaStream_t)stream);
+}
+
+int pdr_point_visibility(const float* point_uvs, const float* point_depths,
+                         const float* mesh_depths, int V, int N, int cam_res, float offset,
+                         int res, uint8_t* vis, long long* pix_cam, long long* pix_res,
+                         void* stream) {
+  PDR_CHECK_ARG(point_uvs != nullptr, "pdr_point_visibility: null pointer");
+  return point_visibility_launch(point_uvs, point_depths, mesh_depths, V, N, cam_res, offset, res,
+                                 vis, pix_cam, pix_res, (cudaStream_t)stream);
+}
+
+size_t pdr_sparse_images_workspace_bytes(int V, int res) {
+  return sparse_images_workspace_bytes(V, res);
+}
+int pdr_sparse_images(const long long* point_pixels, const float* colors, const uint8_t* valid,
+                      const uint8_t* hard_masks, int V, int N, int res, int point_size,
+                      int edge_point_size, double mask_ratio_thresh, void* workspace,
+                      float* sparse, float* hard_mask0, float* hard_mask2, float* scale_factors,
+                      void* stream) {
+  PDR_CHECK_ARG(point_pixels && colors && valid && hard_masks && workspace && sparse &&
+                    hard_mask0 && hard_mask2 && scale_factors,
+                "pdr_sparse_images: null pointer");
+  return sparse_images_launch(point_pixels, colors, valid, hard_masks, V, N, res, point_size,
+                              edge_point_size, mask_ratio_thresh, workspace, sparse, hard_mask0,
+                              hard_mask2, scale_factors, (cudaStream_t)stream);
+}
+
+size_t pdr_nearest_fill_workspace_bytes(int B, int H, int W) {
+  return nearest_fill_workspace_bytes(B, H, W);
+}
+int pdr_nearest_fill(const float* img, const uint8_t* known, int B, int C, int H, int W,
+                     int channels_last, void* workspace, float* out, int* src_index,
+                     void* stream) {
+  PDR_CHECK_ARG(img && known && workspace && out, "pdr_nearest_fill: null pointer");
+  return nearest_fill_launch(img, known, B, C, H, W, channels_last, workspace, out, src_index,
+                             (cudaStream_t)stream);
+}
+
+size_t pdr_unproject_workspace_bytes(int R, int n_levels) {
+  return unproject_workspace_bytes(R, n_levels);
+}
+int pdr_unproject(const float* images, int res, const float* cam_params, int V, int cam_res,
+                  const float* base_dirs, const float* gb_pos, const uint8_t* mask,
+                  const long long* face_id, int R, const float* f_normals, int F,
+                  const float* uv_centers, const float* uv_scales, double padding, int rescale,
+                  const float* scale_factors, const float* mesh_depths, const int* kernels_host,
+                  int n_levels, int complete_unseen, void* workspace, float* atlas,
+                  uint8_t* shrinked_vis, long long* point_view_ids, long long* point_coords,
+                  float* points, uint8_t* painted, void* stream) {
+  PDR_CHECK_ARG(images && cam_params && base_dirs && gb_pos && mask && face_id && f_normals &&
+                    mesh_depths && kernels_host && workspace && atlas && painted,
+                "pdr_unproject: null pointer");
+  PDR_CHECK_ARG(!rescale || (uv_centers && uv_scales && scale_factors),
+                "pdr_unproject: rescale requested without uv_centers/uv_scales/scale_factors");
+  return unproject_launch(images, res, cam_params, V, cam_res, base_dirs, gb_pos, mask, face_id, R,
+                          f_normals, F, uv_centers, uv_scales, padding, rescale, scale_factors,
+                          mesh_depths, kernels_host, n_levels, n_levels, complete_unseen,
+                          workspace, atlas, shrinked_vis, point_view_ids, point_coords, points,
+                          painted, (cudaStream_t)stream);
+}
+int pdr_mask_count(const uint8_t* mask, size_t n, int* ws_counter, int* out_host, void* stream) {
+  PDR_CHECK_ARG(mask && ws_counter && out_host, "pdr_mask_count: null pointer");
+  return mask_count_sync(mask, n, ws_counter, out_host, (cudaStream_t)stream);
 }
 
 }  // extern "C"

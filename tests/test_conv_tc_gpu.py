@@ -20,8 +20,8 @@ def _run(cuda, B, H, W, C1, C2, Cout, taps, bn, bias=True, residual=False, seed=
     out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=cuda)
     # [Cout][tap][C]
     wk = w.permute(0, 2, 3, 1).reshape(Cout, taps * C).contiguous()
-    _lib.call("pdr_conv_tc", _lib.ptr(x1), _lib.ptr(x2), _lib.ptr(wk), _lib.ptr(b), _lib.ptr(res),
-              _lib.ptr(out), B, H, W, C1, C2, Cout, taps, bn)
+    _lib.call("pdr_conv_tc", x1, x2, wk, b, res,
+              out, B, H, W, C1, C2, Cout, taps, bn)
     torch.cuda.synchronize()
     xin = x1 if x2 is None else torch.cat([x1, x2], -1)
     ref = F.conv2d(xin.float().permute(0, 3, 1, 2), w.float(), b, padding=k // 2)

@@ -26,7 +26,7 @@ for (B, H, W, C1, C2, Cout, taps) in shapes:
         w = (torch.randn(Cout, taps * (C1 + C2), device=dev) * 0.02).half()
         b = torch.randn(Cout, device=dev)
         out = torch.empty(B, H, W, Cout, device=dev, dtype=torch.float16)
-        args = (_lib.ptr(x1), _lib.ptr(x2), _lib.ptr(w), _lib.ptr(b), _lib.ptr(None), _lib.ptr(out),
+        args = (x1, x2, w, b, None, out,
                 B, H, W, C1, C2, Cout, taps, bn)
         for _ in range(3):
             _lib.call("pdr_conv_tc", *args)
