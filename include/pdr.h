@@ -38,10 +38,90 @@ unsigned long long pdr_launch_count(void);
  *   x1 [B,H,W,C1] fp16, x2 [B,H,W,C2] fp16 or NULL (channel concat, unet.py:660-662)
  *   w  [Cout][taps*(C1+C2)] fp16, K index = tap*(C1+C2)+c, tap = ky*3+kx
  *   bias [Cout] fp32 or NULL; residual [B,H,W,Cout] fp16 or NULL; out [B,H,W,Cout] fp16
- *   bn: N tile, 128 / 256 / 0 (auto).  C1, C2 % 64 == 0, Cout % 128 == 0. */
+ *   bn: N tile, 64 / 128 / 256 / 0 (auto), must divide Cout.  C1, C2, Cout % 64 == 0. */
 int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias,
                 const void* residual, void* out, int B, int H, int W, int C1, int C2, int Cout,
                 int taps, int bn, void* stream);
+
+/* Individual non-GEMM U-Net kernels (exported for unit parity tests; the engine below calls the
+ * same launchers).  NHWC fp16 activations, fp32 parameters.
+ *   pdr_linear: out[b][n] = bias[n] + sum_k f(in[b][k]) W[n][k]; mode_in 0 id, 1 SiLU,
+ *               2 in = timestep_embedding(t[b], K)  (nn.py:103-121; unet.py:450-455, 199-205)
+ *   pdr_stem_conv: x [B,3,H,W] fp32 -> fp16 -> conv3x3 -> [B,H,W,C] fp16   (unet.py:482-484,655)
+ *   pdr_group_norm: GroupNorm32(32 groups) of cat(x1,x2) (+FiLM (1+scale),shift from
+ *               film[b][film_off + {c, C+c}]) (+SiLU) (+resample 1=avgpool2, 2=nearest x2)
+ *               (nn.py:17-19, unet.py:236-252);  ws: float[B*slabs*2*C], stats: float[B*64]
+ *   pdr_resample: avg-pool 2 (mode 1) / nearest x2 (mode 2)                  (unet.py:92-140)
+ *   pdr_attention: QKVAttentionLegacy on qkv [B,T,3C] -> [B,T,C], head dim 64 (unet.py:328-358)
+ *   pdr_unet_head: GN + SiLU + conv3x3(C -> n_out) in fp32, NCHW fp32 output  (unet.py:613-617)*/
+int pdr_linear(const float* in, const float* W, const float* bias, int B, int K, int N,
+               int mode_in, float* out, void* out_fp16, void* stream);
+int pdr_stem_conv(const float* x, const void* w, const float* bias, int B, int H, int W, int C,
+                  void* out, void* stream);
+int pdr_group_norm(const void* x1, const void* x2, int B, int H, int W, int C1, int C2,
+                   const float* gamma, const float* beta, const void* film, int film_stride,
+                   int film_off, int silu, int resample, float* ws, float* stats, void* out,
+                   void* stream);
+int pdr_resample(const void* x, int B, int H, int W, int C, int mode, void* out, void* stream);
+int pdr_attention(const void* qkv, int B, int T, int heads, void* out, void* stream);
+int pdr_unet_head(const void* h, const float* gamma, const float* beta, const float* w,
+                  const float* bias, int B, int H, int W, int C, int n_out, float* ws,
+                  float* stats, float* out, void* stream);
+
+/* --------------------------------------------------------- U-Net engine + DDNM ---------- */
+/* Structure of the ADM U-Net, the arguments of script_util.create_model (script_util.py:130-185)
+ * as resolved from models/DDNM/configs/imagenet_256.yml. channel_mult is stored doubled so the
+ * 512-pixel preset's 0.5 is representable. */
+typedef struct PdrUnetConfig {
+  int image_size, in_channels, model_channels, out_channels, num_res_blocks;
+  int n_mult, channel_mult_x2[8];
+  int n_attn_ds, attn_ds[8]; /* downsample factors that carry attention */
+  int num_head_channels;
+} PdrUnetConfig;
+
+/* Replaces Diffusion.get_model / create_model + convert_to_fp16 (diffusion.py:435-457).
+ * Parameters are registered under the reference's state_dict names:
+ *   conv weights  fp16 [Cout][taps*Cin] (tap-major: K = (ky*3+kx)*Cin + c), biases fp32;
+ *   GroupNorm / Linear / out.2 parameters fp32 in PyTorch layout;
+ *   "emb_all.weight" [sum 2*Cout, 4*mc] / "emb_all.bias": every ResBlock's emb_layers.1
+ *   concatenated in module order (input_blocks, middle_block, output_blocks). */
+int pdr_unet_create(const PdrUnetConfig* cfg, void** handle);
+int pdr_unet_destroy(void* handle);
+int pdr_unet_set_param(void* handle, const char* name, const void* ptr, size_t bytes);
+int pdr_unet_workspace_bytes(void* handle, int B, size_t* bytes);
+int pdr_unet_plan(void* handle, int B, void* workspace, size_t bytes);
+/* UNetModel.forward (unet.py:635-664): x [B,3,S,S] fp32, t [B] fp32 -> out [B,n_out,S,S] fp32 */
+int pdr_unet_forward(void* handle, const float* x, const float* t, float* out, int n_out,
+                     void* stream);
+
+/* torch.randn-compatible standard normals (Philox4x32-10 + Box-Muller, torch's thread mapping):
+ * out[numel] == torch.randn(numel, device='cuda') drawn with (seed, philox offset). */
+int pdr_randn_like_torch(float* out, long long numel, unsigned long long seed,
+                         unsigned long long offset, void* stream);
+/* philox offset increment of one torch.randn(numel) call on this device */
+unsigned long long pdr_randn_offset_increment(long long numel);
+
+/* Diffusion.simplified_ddnm_inpainting (diffusion.py:459-570) for V chains at once.
+ *   sparse [V,3,S,S] fp32 in [0,1]; mask [V,S,S] fp32 (1 = known)
+ *   coef_host: HOST float[steps][7] = sqrt(1-at), sqrt(at), sqrt(at_next), gamma_t, c1, c2, lambda_t
+ *   t_dev: float[steps][V] (timestep fed to the U-Net at every step)
+ *   noise of chain v, draw d comes from torch's global-generator stream at draw index
+ *   (chain0 + v)*draws_per_chain + d  (d = 0: x_T, d = 1+s: step s), see SURVEY Appendix C
+ *   x, y: float[V*3*S*S] scratch; et: float[V*3*S*S] scratch; out [V,3,S,S] fp32 in [0,1] */
+int pdr_ddnm_sample(void* unet, const float* sparse, const float* mask, int V, int steps,
+                    const float* coef_host, const float* t_dev, unsigned long long seed,
+                    unsigned long long offset_base, unsigned long long draws_per_chain,
+                    int chain0, float* x, float* y, float* et, float* out, void* stream);
+/* single pieces of the sampler (exported for parity tests) */
+int pdr_ddnm_prepare(const float* sparse, const float* mask, int V, int S,
+                     unsigned long long seed, unsigned long long offset_base,
+                     unsigned long long draws_per_chain, int chain0, float* y, float* x,
+                     void* stream);
+int pdr_ddnm_step(float* x, const float* et, int et_channels, const float* y, const float* mask,
+                  int V, int S, const float* coef7_host, unsigned long long seed,
+                  unsigned long long offset_base, unsigned long long draws_per_chain, int chain0,
+                  int draw_index, void* stream);
+int pdr_ddnm_final(const float* x, long long n, float* out, void* stream);
 
 /* --------------------------------------------------------------- PROJECT --------------- */
 /* Camera transform + crop/rescale of mesh vertices and cloud points for all V views.

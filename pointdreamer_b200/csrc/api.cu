@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "conv_tc.h"
 #include "geom.h"
+#include "unet_engine.h"
+#include "unet_ops.h"
 
 using namespace pdr;
 
@@ -17,7 +19,7 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
                 int taps, int bn, void* stream) {
   PDR_CHECK_ARG(x1 && w && out, "pdr_conv_tc: null pointer");
   PDR_CHECK_ARG(B > 0 && H > 0 && W > 0, "pdr_conv_tc: empty shape");
-  PDR_CHECK_ARG(Cout % 128 == 0, "pdr_conv_tc: Cout (%d) must be a multiple of 128", Cout);
+  PDR_CHECK_ARG(Cout % 64 == 0, "pdr_conv_tc: Cout (%d) must be a multiple of 64", Cout);
   if (bn == 0) bn = conv_tc_pick_bn(B, H, W, Cout);
   ConvTensorMap ma1, ma2, mw;
   PDR_TRY(conv_tc_make_act_map(&ma1, x1, B, H, W, C1));
@@ -28,6 +30,105 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
   PDR_TRY(conv_tc_make_weight_map(&mw, w, Cout, taps * (C1 + C2), bn));
   return conv_tc_launch(&ma1, C2 > 0 ? &ma2 : nullptr, &mw, bn, B, H, W, C1, C2, Cout, taps, bias,
                         (const __half*)residual, (__half*)out, (cudaStream_t)stream);
+}
+
+int pdr_linear(const float* in, const float* W, const float* bias, int B, int K, int N,
+               int mode_in, float* out, void* out_fp16, void* stream) {
+  PDR_CHECK_ARG(in && W && (out || out_fp16), "pdr_linear: null pointer");
+  return linear_launch(in, W, bias, B, K, N, mode_in, out, (__half*)out_fp16,
+                       (cudaStream_t)stream);
+}
+int pdr_stem_conv(const float* x, const void* w, const float* bias, int B, int H, int W, int C,
+                  void* out, void* stream) {
+  PDR_CHECK_ARG(x && w && bias && out, "pdr_stem_conv: null pointer");
+  return stem_conv_launch(x, (const __half*)w, bias, B, H, W, C, (__half*)out,
+                          (cudaStream_t)stream);
+}
+int pdr_group_norm(const void* x1, const void* x2, int B, int H, int W, int C1, int C2,
+                   const float* gamma, const float* beta, const void* film, int film_stride,
+                   int film_off, int silu, int resample, float* ws, float* stats, void* out,
+                   void* stream) {
+  PDR_CHECK_ARG(x1 && gamma && beta && ws && stats && out, "pdr_group_norm: null pointer");
+  PDR_TRY(gn_stats_launch((const __half*)x1, (const __half*)x2, B, H * W, C1, C2, ws, stats,
+                          (cudaStream_t)stream));
+  return gn_apply_launch((const __half*)x1, (const __half*)x2, B, H, W, C1, C2, stats, gamma, beta,
+                         (const __half*)film, film_stride, film_off, silu, resample, (__half*)out,
+                         (cudaStream_t)stream);
+}
+int pdr_resample(const void* x, int B, int H, int W, int C, int mode, void* out, void* stream) {
+  PDR_CHECK_ARG(x && out, "pdr_resample: null pointer");
+  return resample_launch((const __half*)x, B, H, W, C, mode, (__half*)out, (cudaStream_t)stream);
+}
+int pdr_attention(const void* qkv, int B, int T, int heads, void* out, void* stream) {
+  PDR_CHECK_ARG(qkv && out, "pdr_attention: null pointer");
+  return attention_launch((const __half*)qkv, B, T, heads, (__half*)out, (cudaStream_t)stream);
+}
+int pdr_unet_head(const void* h, const float* gamma, const float* beta, const float* w,
+                  const float* bias, int B, int H, int W, int C, int n_out, float* ws,
+                  float* stats, float* out, void* stream) {
+  PDR_CHECK_ARG(h && gamma && beta && w && bias && ws && stats && out, "pdr_unet_head: null");
+  PDR_TRY(gn_stats_launch((const __half*)h, nullptr, B, H * W, C, 0, ws, stats,
+                          (cudaStream_t)stream));
+  return head_launch((const __half*)h, stats, gamma, beta, w, bias, B, H, W, C, n_out, out, n_out,
+                     (cudaStream_t)stream);
+}
+
+int pdr_unet_create(const PdrUnetConfig* cfg, void** handle) { return unet_create(cfg, handle); }
+int pdr_unet_destroy(void* handle) { return unet_destroy(handle); }
+int pdr_unet_set_param(void* handle, const char* name, const void* ptr, size_t bytes) {
+  return unet_set_param(handle, name, ptr, bytes);
+}
+int pdr_unet_workspace_bytes(void* handle, int B, size_t* bytes) {
+  return unet_workspace_bytes(handle, B, bytes);
+}
+int pdr_unet_plan(void* handle, int B, void* workspace, size_t bytes) {
+  return unet_plan(handle, B, workspace, bytes);
+}
+int pdr_unet_forward(void* handle, const float* x, const float* t, float* out, int n_out,
+                     void* stream) {
+  return unet_forward(handle, x, t, out, n_out, (cudaStream_t)stream);
+}
+
+int pdr_randn_like_torch(float* out, long long numel, unsigned long long seed,
+                         unsigned long long offset, void* stream) {
+  PDR_CHECK_ARG(out && numel > 0, "pdr_randn_like_torch: bad argument");
+  return randn_like_torch_launch(out, numel, seed, offset, (cudaStream_t)stream);
+}
+unsigned long long pdr_randn_offset_increment(long long numel) {
+  long long T;
+  unsigned long long inc;
+  philox_launch_geometry(numel, &T, &inc);
+  return inc;
+}
+int pdr_ddnm_sample(void* unet, const float* sparse, const float* mask, int V, int steps,
+                    const float* coef_host, const float* t_dev, unsigned long long seed,
+                    unsigned long long offset_base, unsigned long long draws_per_chain,
+                    int chain0, float* x, float* y, float* et, float* out, void* stream) {
+  return ddnm_sample(unet, sparse, mask, V, steps, coef_host, t_dev, seed, offset_base,
+                     draws_per_chain, chain0, x, y, et, out, (cudaStream_t)stream);
+}
+int pdr_ddnm_prepare(const float* sparse, const float* mask, int V, int S,
+                     unsigned long long seed, unsigned long long offset_base,
+                     unsigned long long draws_per_chain, int chain0, float* y, float* x,
+                     void* stream) {
+  PDR_CHECK_ARG(sparse && mask && y && x, "pdr_ddnm_prepare: null pointer");
+  return ddnm_prepare_launch(sparse, mask, V, 3, S, S, seed, offset_base, draws_per_chain, chain0,
+                             y, x, (cudaStream_t)stream);
+}
+int pdr_ddnm_step(float* x, const float* et, int et_channels, const float* y, const float* mask,
+                  int V, int S, const float* c, unsigned long long seed,
+                  unsigned long long offset_base, unsigned long long draws_per_chain, int chain0,
+                  int draw_index, void* stream) {
+  PDR_CHECK_ARG(x && et && y && mask && c, "pdr_ddnm_step: null pointer");
+  DdnmStepCoef k;
+  k.sqrt_1m_at = c[0], k.sqrt_at = c[1], k.sqrt_at_next = c[2], k.gamma_t = c[3];
+  k.c1 = c[4], k.c2 = c[5], k.lambda_t = c[6];
+  return ddnm_step_launch(x, et, et_channels, y, mask, V, 3, S, S, k, seed, offset_base,
+                          draws_per_chain, chain0, draw_index, (cudaStream_t)stream);
+}
+int pdr_ddnm_final(const float* x, long long n, float* out, void* stream) {
+  PDR_CHECK_ARG(x && out, "pdr_ddnm_final: null pointer");
+  return ddnm_final_launch(x, n, out, (cudaStream_t)stream);
 }
 
 int pdr_project(const float* cam_params, const float* vertices, int Vm, const float* points,

@@ -322,13 +322,19 @@ int conv_tc_make_weight_map(ConvTensorMap* out, const void* ptr, int Cout, int K
 }
 
 int conv_tc_pick_bn(int B, int H, int W, int Cout) {
-  // BN = 256 halves A re-reads; fall back to 128 when that leaves SMs idle.
-  if (Cout % 256 != 0) return 128;
+  // Largest N tile that divides Cout (fewer A re-reads); step down while SMs would sit idle.
   int bw, bh, bb;
   conv_tc_pick_box(B, H, W, &bw, &bh, &bb);
-  long long tiles_m = (long long)cdiv(B, bb) * (H / bh) * (W / bw);
-  if (tiles_m * (Cout / 256) < num_sms()) return 128;
-  return 256;
+  const long long tiles_m = (long long)cdiv(B, bb) * (H / bh) * (W / bw);
+  int best = 0;
+  for (int bn = 256; bn >= 64; bn >>= 1) {
+    if (Cout % bn != 0) continue;
+    if (best == 0) best = bn;
+    if (tiles_m * (Cout / bn) >= num_sms()) return bn;
+    best = bn;  // keep shrinking: more tiles for a layer that cannot fill the machine
+    if (bn == 128) break;  // BN=64 only when Cout demands it
+  }
+  return best;
 }
 
 template <int BN, int STAGES>
@@ -356,7 +362,7 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
                    const float* bias, const __half* residual, __half* out, cudaStream_t stream) {
   PDR_CHECK_ARG(taps == 9 || taps == 1, "taps must be 9 or 1 (got %d)", taps);
   PDR_CHECK_ARG(C1 > 0 && C1 % BLOCK_K == 0 && C2 % BLOCK_K == 0, "C1/C2 must be multiples of 64");
-  PDR_CHECK_ARG(BN == 128 || BN == 256, "BN must be 128 or 256");
+  PDR_CHECK_ARG(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256");
   PDR_CHECK_ARG(Cout % BN == 0, "Cout (%d) must be a multiple of BN (%d)", Cout, BN);
   PDR_CHECK_ARG(C2 == 0 || a2 != nullptr, "second A tensor map missing");
   ConvArgs args;
@@ -378,7 +384,8 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   args.residual = residual;
   args.out = out;
   if (BN == 256) return launch_impl<256, 4>(a1, a2, w, args, stream);
-  return launch_impl<128, 6>(a1, a2, w, args, stream);
+  if (BN == 128) return launch_impl<128, 6>(a1, a2, w, args, stream);
+  return launch_impl<64, 8>(a1, a2, w, args, stream);
 }
 
 }  // namespace pdr

@@ -1,0 +1,549 @@
+// Memory-bound glue kernels of the ADM U-Net (everything that is not a tensor-core GEMM):
+// time embedding MLP + per-ResBlock emb_layers (fp32), stem conv 3->C, GroupNorm32 statistics
+// and apply (+SiLU, +FiLM scale/shift, +AvgPool2/nearest-up2 resampling, two-source concat),
+// plain resampling, and the fp32 output head (GN + SiLU + conv C->6).
+//
+// Reference: models/DDNM/guided_diffusion/unet.py (ResBlock._forward 236-256,
+// UNetModel.forward 635-664, Upsample 92-110, Downsample 113-140), nn.py (GroupNorm32 17-19,
+// timestep_embedding 103-121).  Activations are NHWC fp16; rounding to fp16 happens at exactly
+// the points where the reference materialises an fp16 tensor (see oracle/unet.py).
+#include "common.cuh"
+#include "unet_ops.h"
+
+namespace pdr {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float h2f(__half h) { return __half2float(h); }
+__device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
+
+// ------------------------------------------------------------ linear (fp32) ----
+// out[b][n] = bias[n] + sum_k f(in[b][k]) * W[n][k];  f = identity | SiLU | timestep embedding.
+// One warp per output feature, all (<= 8) batch rows at once; in[] staged in shared memory.
+// mode_in: 0 identity, 1 SiLU(in), 2 in = timestep_embedding(t[b], K)   (nn.py:103-121)
+// mode_out: 0 fp32, 1 fp32 SiLU(out)... only 0 used; out16 != null additionally stores fp16.
+__global__ void linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
+                              const float* __restrict__ bias, int B, int K, int N, int mode_in,
+                              float* __restrict__ out, __half* __restrict__ out16) {
+  extern __shared__ float s_in[];  // [bchunk<=8][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    const int nb = min(8, B - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * K; i += blockDim.x) {
+      const int b = i / K, k = i - b * K;
+      float v;
+      if (mode_in == 2) {
+        const int half = K / 2;
+        const int j = k < half ? k : k - half;
+        const float freq = expf((-9.210340371976184f * (float)j) / (float)half);
+        const float a = in[b0 + b] * freq;
+        v = k < half ? cosf(a) : sinf(a);
+      } else {
+        v = in[(size_t)(b0 + b) * K + k];
+        if (mode_in == 1) v = silu_f(v);
+      }
+      s_in[i] = v;
+    }
+    __syncthreads();
+    for (int n = blockIdx.x * warps + warp; n < N; n += gridDim.x * warps) {
+      float acc[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[b] = 0.f;
+      const float* wr = W + (size_t)n * K;
+      for (int k = lane * 4; k < K; k += 128) {
+        const float4 w4 = __ldg((const float4*)(wr + k));
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (b < nb) {
+            const float* s = s_in + b * K + k;
+            acc[b] += w4.x * s[0] + w4.y * s[1] + w4.z * s[2] + w4.w * s[3];
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+      if (lane == 0) {
+        const float bv = bias ? bias[n] : 0.f;
+        for (int b = 0; b < nb; ++b) {
+          const float r = acc[b] + bv;
+          if (out) out[(size_t)(b0 + b) * N + n] = r;
+          if (out16) out16[(size_t)(b0 + b) * N + n] = __float2half_rn(r);
+        }
+      }
+    }
+  }
+}
+
+int linear_launch(const float* in, const float* W, const float* bias, int B, int K, int N,
+                  int mode_in, float* out, __half* out16, cudaStream_t stream) {
+  PDR_CHECK_ARG(K % 4 == 0 && K <= 4096, "linear: K=%d must be a multiple of 4 and <= 4096", K);
+  const int threads = 256;
+  const int nbk = B < 8 ? B : 8;
+  const size_t smem = (size_t)nbk * K * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    PDR_CUDA(cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  8 * 4096 * 4));
+    configured = true;
+  }
+  int grid = cdiv(N, threads / 32);
+  if (grid > 148 * 8) grid = 148 * 8;
+  linear_kernel<<<grid, threads, smem, stream>>>(in, W, bias, B, K, N, mode_in, out, out16);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- stem conv ----
+// x [B,3,H,W] fp32 NCHW -> fp16 (unet.py:655) -> conv3x3(3->C) -> NHWC fp16.
+// A warp produces one pixel's C-vector at a time (lane = 8-channel chunk): coalesced 16-B stores.
+__global__ void stem_conv_kernel(const float* __restrict__ x, const __half* __restrict__ w,
+                                 const float* __restrict__ bias, int B, int H, int W, int C,
+                                 __half* __restrict__ out) {
+  extern __shared__ float s_w[];  // [27][C]
+  for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) {
+    const int k = i / C, c = i - k * C;
+    s_w[i] = h2f(w[(size_t)c * 27 + k]);  // w is [C][tap*3 + cin]
+  }
+  __syncthreads();
+  const int chunks = C / 8;
+  const int lane_chunk = threadIdx.x % chunks;
+  const int pix_in_block = threadIdx.x / chunks;
+  const int pix_per_block = blockDim.x / chunks;
+  const size_t npix = (size_t)B * H * W;
+  for (size_t p = (size_t)blockIdx.x * pix_per_block + pix_in_block; p < npix;
+       p += (size_t)gridDim.x * pix_per_block) {
+    const int xw = p % W, yh = (p / W) % H, b = p / ((size_t)W * H);
+    float in[27];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = yh + ky - 1, xx = xw + kx - 1;
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          in[(ky * 3 + kx) * 3 + c] =
+              ok ? round_h(__ldg(x + (((size_t)b * 3 + c) * H + yy) * W + xx)) : 0.f;
+      }
+    float acc[8];
+    const int c0 = lane_chunk * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4 w0 = *(const float4*)(s_w + k * C + c0);
+      const float4 w1 = *(const float4*)(s_w + k * C + c0 + 4);
+      acc[0] += in[k] * w0.x, acc[1] += in[k] * w0.y, acc[2] += in[k] * w0.z, acc[3] += in[k] * w0.w;
+      acc[4] += in[k] * w1.x, acc[5] += in[k] * w1.y, acc[6] += in[k] * w1.z, acc[7] += in[k] * w1.w;
+    }
+    __align__(16) __half o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(acc[j] + bias[c0 + j]);
+    *(uint4*)(out + p * C + c0) = *(const uint4*)o;
+  }
+}
+
+int stem_conv_launch(const float* x, const __half* w, const float* bias, int B, int H, int W,
+                     int C, __half* out, cudaStream_t stream) {
+  PDR_CHECK_ARG(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "stem: unsupported C=%d", C);
+  const size_t smem = (size_t)27 * C * sizeof(float);
+  PDR_CHECK_ARG(smem <= 200 * 1024, "stem: C too large");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    PDR_CUDA(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    configured = smem;
+  }
+  const int ppb = 256 / (C / 8);
+  long long blocks = cdiv((long long)B * H * W, ppb);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stem_conv_kernel<<<(int)blocks, 256, smem, stream>>>(x, w, bias, B, H, W, C, out);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------ GroupNorm32 ----
+// statistics: per-(batch, slab, channel) partial sum / sum of squares in fp32, finalised in
+// double per (batch, group).  x = concat(x1[C1], x2[C2]) along channels, NHWC fp16.
+__device__ __forceinline__ const __half* src_ptr(const __half* x1, const __half* x2, int C1,
+                                                 int C2, size_t pixel, int c) {
+  return c < C1 ? x1 + pixel * C1 + c : x2 + pixel * C2 + (c - C1);
+}
+
+__global__ void gn_partial_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2,
+                                  int C1, int C2, int HW, int slabs,
+                                  float* __restrict__ partial) {
+  // grid (slabs, B); thread -> (pixel lane, 8-channel chunk)
+  const int C = C1 + C2;
+  const int chunks = C / 8;
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int chunk = threadIdx.x % chunks;
+  const int plane = threadIdx.x / chunks;
+  const int planes = blockDim.x / chunks;
+  const int per_slab = (HW + slabs - 1) / slabs;
+  const int p0 = slab * per_slab, p1 = min(HW, p0 + per_slab);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  const int c0 = chunk * 8;
+  if (plane < planes) {
+    for (int p = p0 + plane; p < p1; p += planes) {
+      const uint4 v = __ldg((const uint4*)src_ptr(x1, x2, C1, C2, (size_t)b * HW + p, c0));
+      const __half* h = (const __half*)&v;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f = h2f(h[j]);
+        s[j] += f;
+        q[j] += f * f;
+      }
+    }
+  }
+  // deterministic block reduction: per-plane partials, summed in plane order
+  extern __shared__ float sm[];  // [planes][2][C]
+  if (plane < planes) {
+    float* mine = sm + (size_t)plane * 2 * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mine[c0 + j] = s[j];
+      mine[C + c0 + j] = q[j];
+    }
+  }
+  __syncthreads();
+  float* dst = partial + ((size_t)b * slabs + slab) * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float acc = 0.f;
+    for (int p = 0; p < planes; ++p) acc += sm[(size_t)p * 2 * C + i];
+    dst[i] = acc;
+  }
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int C, int HW, int slabs,
+                                   float eps, float* __restrict__ stats) {
+  // one warp per (b, group)
+  const int b = blockIdx.y, g = blockIdx.x;
+  const int cpg = C / 32;
+  double s = 0.0, q = 0.0;
+  const int n = slabs * cpg;
+  for (int i = threadIdx.x; i < n; i += 32) {
+    const int slab = i / cpg, c = g * cpg + i % cpg;
+    const float* src = partial + ((size_t)b * slabs + slab) * 2 * C;
+    s += (double)src[c];
+    q += (double)src[C + c];
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (threadIdx.x == 0) {
+    const double cnt = (double)HW * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((size_t)b * 32 + g) * 2 + 0] = (float)mean;
+    stats[((size_t)b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+int gn_stats_slabs(int B, int HW) {
+  // Depends on the image size only: the summation order (and so every bit of the result) of a
+  // chain is the same whatever batch it runs in.
+  (void)B;
+  int slabs = (HW + 255) / 256;
+  if (slabs > 74) slabs = 74;
+  if (slabs < 1) slabs = 1;
+  return slabs;
+}
+
+int gn_stats_launch(const __half* x1, const __half* x2, int B, int HW, int C1, int C2,
+                    float* ws_partial, float* stats, cudaStream_t stream) {
+  const int C = C1 + C2;
+  PDR_CHECK_ARG(C % 32 == 0 && C1 % 8 == 0 && C2 % 8 == 0 && C <= 4096,
+                "GroupNorm32: unsupported channel count %d+%d", C1, C2);
+  const int chunks = C / 8;
+  const int threads = chunks >= 256 ? chunks : 256 / chunks * chunks;
+  PDR_CHECK_ARG(threads <= 1024, "GroupNorm32: too many channels");
+  const int slabs = gn_stats_slabs(B, HW);
+  gn_partial_kernel<<<dim3(slabs, B), threads, (size_t)(threads / chunks) * 2 * C * sizeof(float),
+                      stream>>>(
+      x1, x2 ? x2 : x1, C1, C2, HW, slabs, ws_partial);
+  PDR_COUNT_LAUNCH();
+  gn_finalize_kernel<<<dim3(32, B), 32, 0, stream>>>(ws_partial, C, HW, slabs, 1e-5f, stats);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+// apply: y = GN(x)*gamma+beta  [-> fp16] [ *(1+scale)+shift -> fp16 ] [ SiLU -> fp16 ]
+//        [ AvgPool2 / nearest-up2 ]  -> out NHWC fp16 [B,Ho,Wo,C]
+// resample: 0 none, 1 down (avg 2x2), 2 up (nearest 2x)
+struct GnApplyArgs {
+  const __half* x1;
+  const __half* x2;
+  int C1, C2, B, H, W;
+  const float* stats;    // [B,32,2]
+  const float* gamma;    // [C]
+  const float* beta;     // [C]
+  const __half* film;    // [B, film_stride] fp16: scale at [coff + c], shift at [coff + C + c]
+  int film_stride, film_off;
+  int silu, resample;
+  __half* out;
+};
+
+__device__ __forceinline__ void gn_apply_8(const GnApplyArgs& a, int b, size_t pixel, int c0,
+                                           const float (&ga)[8], const float (&gb)[8],
+                                           const float (&fs)[8], const float (&fsh)[8],
+                                           float (&y)[8]) {
+  const uint4 v = __ldg((const uint4*)src_ptr(a.x1, a.x2, a.C1, a.C2, pixel, c0));
+  const __half* h = (const __half*)&v;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float t = round_h(h2f(h[j]) * ga[j] + gb[j]);      // GroupNorm32 output, fp16
+    if (a.film) t = round_h(round_h(t * fs[j]) + fsh[j]);  // h*(1+scale) -> fp16, +shift -> fp16
+    if (a.silu) t = round_h(silu_f(t));
+    y[j] = t;
+  }
+  (void)b;
+}
+
+__global__ void gn_apply_kernel(const GnApplyArgs a) {
+  const int C = a.C1 + a.C2;
+  const int chunks = C / 8;
+  const int Ho = a.resample == 1 ? a.H / 2 : (a.resample == 2 ? a.H * 2 : a.H);
+  const int Wo = a.resample == 1 ? a.W / 2 : (a.resample == 2 ? a.W * 2 : a.W);
+  const size_t total = (size_t)a.B * Ho * Wo * chunks;
+  const int cpg = C / 32;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int chunk = i % chunks;
+    const size_t po = i / chunks;
+    const int xo = po % Wo, yo = (po / Wo) % Ho, b = po / ((size_t)Wo * Ho);
+    const int c0 = chunk * 8;
+    float ga[8], gb[8], fs[8], fsh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const int g = c / cpg;
+      const float mean = a.stats[((size_t)b * 32 + g) * 2], rstd = a.stats[((size_t)b * 32 + g) * 2 + 1];
+      const float w = a.gamma[c];
+      ga[j] = rstd * w;
+      gb[j] = a.beta[c] - mean * ga[j];
+      if (a.film) {
+        const __half* f = a.film + (size_t)b * a.film_stride + a.film_off;
+        fs[j] = round_h(1.0f + h2f(f[c]));  // (1 + scale) in fp16
+        fsh[j] = h2f(f[C + c]);
+      } else {
+        fs[j] = 1.f, fsh[j] = 0.f;
+      }
+    }
+    float y[8];
+    if (a.resample == 1) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t pin = ((size_t)b * a.H + (2 * yo + dy)) * a.W + (2 * xo + dx);
+          gn_apply_8(a, b, pin, c0, ga, gb, fs, fsh, y);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += y[j];
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = acc[j] * 0.25f;
+    } else if (a.resample == 2) {
+      const size_t pin = ((size_t)b * a.H + (yo >> 1)) * a.W + (xo >> 1);
+      gn_apply_8(a, b, pin, c0, ga, gb, fs, fsh, y);
+    } else {
+      gn_apply_8(a, b, po, c0, ga, gb, fs, fsh, y);
+    }
+    __align__(16) __half o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(y[j]);
+    *(uint4*)(a.out + po * C + c0) = *(const uint4*)o;
+  }
+}
+
+int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int C1, int C2,
+                    const float* stats, const float* gamma, const float* beta,
+                    const __half* film, int film_stride, int film_off, int silu, int resample,
+                    __half* out, cudaStream_t stream) {
+  const int C = C1 + C2;
+  PDR_CHECK_ARG(C % 32 == 0 && C1 % 8 == 0 && C2 % 8 == 0, "GroupNorm32 apply: bad channels");
+  PDR_CHECK_ARG(resample != 1 || (H % 2 == 0 && W % 2 == 0), "avg-pool needs even size");
+  GnApplyArgs a;
+  a.x1 = x1;
+  a.x2 = x2 ? x2 : x1;
+  a.C1 = C1, a.C2 = C2, a.B = B, a.H = H, a.W = W;
+  a.stats = stats, a.gamma = gamma, a.beta = beta;
+  a.film = film, a.film_stride = film_stride, a.film_off = film_off;
+  a.silu = silu, a.resample = resample, a.out = out;
+  const int Ho = resample == 1 ? H / 2 : (resample == 2 ? H * 2 : H);
+  const int Wo = resample == 1 ? W / 2 : (resample == 2 ? W * 2 : W);
+  long long total = (long long)B * Ho * Wo * (C / 8);
+  long long blocks = cdiv(total, 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  gn_apply_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+// plain resampling of x (x_upd in ResBlock._forward, unet.py:241): mode 1 avg-pool 2, 2 nearest x2
+__global__ void resample_kernel(const __half* __restrict__ x, int B, int H, int W, int C, int mode,
+                                __half* __restrict__ out) {
+  const int chunks = C / 8;
+  const int Ho = mode == 1 ? H / 2 : H * 2, Wo = mode == 1 ? W / 2 : W * 2;
+  const size_t total = (size_t)B * Ho * Wo * chunks;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int chunk = i % chunks;
+    const size_t po = i / chunks;
+    const int xo = po % Wo, yo = (po / Wo) % Ho, b = po / ((size_t)Wo * Ho);
+    const int c0 = chunk * 8;
+    __align__(16) __half o[8];
+    if (mode == 1) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int dy = 0; dy < 2; ++dy)
+        for (int dx = 0; dx < 2; ++dx) {
+          const size_t pin = ((size_t)b * H + 2 * yo + dy) * W + 2 * xo + dx;
+          const uint4 v = __ldg((const uint4*)(x + pin * C + c0));
+          const __half* h = (const __half*)&v;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += h2f(h[j]);
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(acc[j] * 0.25f);
+      *(uint4*)(out + po * C + c0) = *(const uint4*)o;
+    } else {
+      const size_t pin = ((size_t)b * H + (yo >> 1)) * W + (xo >> 1);
+      *(uint4*)(out + po * C + c0) = __ldg((const uint4*)(x + pin * C + c0));
+    }
+  }
+}
+
+int resample_launch(const __half* x, int B, int H, int W, int C, int mode, __half* out,
+                    cudaStream_t stream) {
+  PDR_CHECK_ARG(C % 8 == 0 && (mode == 1 || mode == 2), "resample: bad arguments");
+  const int Ho = mode == 1 ? H / 2 : H * 2, Wo = mode == 1 ? W / 2 : W * 2;
+  long long blocks = cdiv((long long)B * Ho * Wo * (C / 8), 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  resample_kernel<<<(int)blocks, 256, 0, stream>>>(x, B, H, W, C, mode, out);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+// --------------------------------------------------------------- fp32 head ----
+// unet.py:663-664: h.float() -> GroupNorm -> SiLU -> conv3x3(C -> n_out) in fp32, NCHW fp32 out.
+// Block = 8 rows x 32 cols of output pixels, thread = 4 consecutive pixels of a row;
+// channels are streamed through shared memory in chunks of HEAD_CC.
+static constexpr int HEAD_CC = 16;
+static constexpr int HEAD_TW = 32, HEAD_TH = 8;
+
+__global__ void __launch_bounds__(64)
+head_kernel(const __half* __restrict__ h, const float* __restrict__ stats,
+            const float* __restrict__ gamma, const float* __restrict__ beta,
+            const float* __restrict__ w, const float* __restrict__ bias, int B, int H, int W,
+            int C, int n_out, float* __restrict__ out, int out_channels_total) {
+  // w: [n_out_total(6)][C][3][3] fp32 (PyTorch layout); only the first n_out rows are used
+  __shared__ float s_act[(HEAD_TH + 2) * (HEAD_TW + 2) * HEAD_CC];
+  __shared__ float s_w[9 * HEAD_CC * 8];  // [tap][cc][8 padded outputs]
+  const int tiles_x = W / HEAD_TW, tiles_y = H / HEAD_TH;
+  const int tile = blockIdx.x;
+  const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+  const int x0 = tx * HEAD_TW, y0 = ty * HEAD_TH;
+  const int tid = threadIdx.x;  // 64 threads: 8 rows x 8 groups of 4 pixels
+  const int row = tid / 8, col4 = (tid % 8) * 4;
+  const int cpg = C / 32;
+  float acc[4][6];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int o = 0; o < 6; ++o) acc[p][o] = 0.f;
+
+  for (int cb = 0; cb < C; cb += HEAD_CC) {
+    __syncthreads();
+    // stage normalised + SiLU activations (zero outside the image = conv zero padding)
+    for (int i = tid; i < (HEAD_TH + 2) * (HEAD_TW + 2) * (HEAD_CC / 8); i += blockDim.x) {
+      const int c8 = i % (HEAD_CC / 8);
+      const int pp = i / (HEAD_CC / 8);
+      const int px = pp % (HEAD_TW + 2), py = pp / (HEAD_TW + 2);
+      const int yy = y0 + py - 1, xx = x0 + px - 1;
+      float v[8];
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const uint4 raw =
+            __ldg((const uint4*)(h + (((size_t)b * H + yy) * W + xx) * C + cb + c8 * 8));
+        const __half* hh = (const __half*)&raw;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = cb + c8 * 8 + j;
+          const int g = c / cpg;
+          const float mean = stats[((size_t)b * 32 + g) * 2], rstd = stats[((size_t)b * 32 + g) * 2 + 1];
+          const float a = rstd * gamma[c];
+          v[j] = silu_f(h2f(hh[j]) * a + (beta[c] - mean * a));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_act[(c8 * 8 + j) * (HEAD_TH + 2) * (HEAD_TW + 2) + pp] = v[j];
+    }
+    for (int i = tid; i < 9 * HEAD_CC * 8; i += blockDim.x) {
+      const int o = i % 8, cc = (i / 8) % HEAD_CC, tap = i / (8 * HEAD_CC);
+      s_w[i] = o < n_out ? w[((size_t)o * C + cb + cc) * 9 + tap] : 0.f;
+    }
+    __syncthreads();
+    for (int cc = 0; cc < HEAD_CC; ++cc) {
+      const float* sa = s_act + cc * (HEAD_TH + 2) * (HEAD_TW + 2);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        float a6[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a6[j] = sa[(row + ky) * (HEAD_TW + 2) + col4 + j];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float4 w0 = *(const float4*)(s_w + ((ky * 3 + kx) * HEAD_CC + cc) * 8);
+          const float4 w1 = *(const float4*)(s_w + ((ky * 3 + kx) * HEAD_CC + cc) * 8 + 4);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float av = a6[p + kx];
+            acc[p][0] += av * w0.x;
+            acc[p][1] += av * w0.y;
+            acc[p][2] += av * w0.z;
+            acc[p][3] += av * w0.w;
+            acc[p][4] += av * w1.x;
+            acc[p][5] += av * w1.y;
+          }
+        }
+      }
+    }
+  }
+  const int y = y0 + row;
+  for (int o = 0; o < n_out; ++o) {
+    float4 r = make_float4(acc[0][o] + bias[o], acc[1][o] + bias[o], acc[2][o] + bias[o],
+                           acc[3][o] + bias[o]);
+    *(float4*)(out + (((size_t)b * out_channels_total + o) * H + y) * W + x0 + col4) = r;
+  }
+}
+
+int head_launch(const __half* h, const float* stats, const float* gamma, const float* beta,
+                const float* w, const float* bias, int B, int H, int W, int C, int n_out,
+                float* out, int out_channels_total, cudaStream_t stream) {
+  PDR_CHECK_ARG(W % HEAD_TW == 0 && H % HEAD_TH == 0, "head: image %dx%d not tileable by %dx%d", H,
+                W, HEAD_TH, HEAD_TW);
+  PDR_CHECK_ARG(C % HEAD_CC == 0 && C % 32 == 0 && n_out >= 1 && n_out <= 6, "head: bad channels");
+  const int tiles = B * (H / HEAD_TH) * (W / HEAD_TW);
+  head_kernel<<<tiles, 64, 0, stream>>>(h, stats, gamma, beta, w, bias, B, H, W, C, n_out, out,
+                                        out_channels_total);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace pdr

@@ -1,0 +1,52 @@
+// Host launchers of the non-GEMM U-Net kernels (unet_ops.cu, attention.cu) and the DDNM sampler
+// kernels (ddnm.cu).  All pointers are device pointers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace pdr {
+
+// out[b][n] = bias[n] + sum_k f(in[b][k]) W[n][k]; mode_in 0 identity, 1 SiLU, 2 timestep embedding
+int linear_launch(const float* in, const float* W, const float* bias, int B, int K, int N,
+                  int mode_in, float* out, __half* out16, cudaStream_t stream);
+
+int stem_conv_launch(const float* x, const __half* w, const float* bias, int B, int H, int W,
+                     int C, __half* out, cudaStream_t stream);
+
+int gn_stats_slabs(int B, int HW);
+// ws_partial: float[B * slabs * 2 * (C1+C2)];  stats: float[B*32*2] (mean, rstd)
+int gn_stats_launch(const __half* x1, const __half* x2, int B, int HW, int C1, int C2,
+                    float* ws_partial, float* stats, cudaStream_t stream);
+int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int C1, int C2,
+                    const float* stats, const float* gamma, const float* beta,
+                    const __half* film, int film_stride, int film_off, int silu, int resample,
+                    __half* out, cudaStream_t stream);
+int resample_launch(const __half* x, int B, int H, int W, int C, int mode, __half* out,
+                    cudaStream_t stream);
+int head_launch(const __half* h, const float* stats, const float* gamma, const float* beta,
+                const float* w, const float* bias, int B, int H, int W, int C, int n_out,
+                float* out, int out_channels_total, cudaStream_t stream);
+
+// qkv [B,T,3C] (legacy head-major layout) -> a [B,T,C]; head dim 64
+int attention_launch(const __half* qkv, int B, int T, int heads, __half* out, cudaStream_t stream);
+
+// ---- DDNM sampler ----
+struct DdnmStepCoef {
+  float sqrt_1m_at, sqrt_at, sqrt_at_next, gamma_t, c1, c2, lambda_t;
+};
+// threads-per-draw / philox counter increment of torch.randn for `numel` on this device
+void philox_launch_geometry(long long numel, long long* threads, unsigned long long* counter_inc);
+int ddnm_prepare_launch(const float* sparse, const float* mask, int V, int C, int H, int W,
+                        unsigned long long seed, unsigned long long offset_base,
+                        unsigned long long draws_per_chain, int chain0, float* y, float* x,
+                        cudaStream_t stream);
+int ddnm_step_launch(float* x, const float* et, int et_channels, const float* y, const float* mask,
+                     int V, int C, int H, int W, DdnmStepCoef coef, unsigned long long seed,
+                     unsigned long long offset_base, unsigned long long draws_per_chain,
+                     int chain0, int draw_index, cudaStream_t stream);
+int ddnm_final_launch(const float* x, long long n, float* out, cudaStream_t stream);
+int randn_like_torch_launch(float* out, long long numel, unsigned long long seed,
+                            unsigned long long offset, cudaStream_t stream);
+
+}  // namespace pdr
