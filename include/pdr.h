@@ -94,6 +94,16 @@ int pdr_unet_plan(void* handle, int B, void* workspace, size_t bytes);
 int pdr_unet_forward(void* handle, const float* x, const float* t, float* out, int n_out,
                      void* stream);
 
+/* Live per-kernel-class timing of the engine (CUDA events on the launching stream around every
+ * launch of each `every`-th forward).  pdr_unet_profile_end synchronises, fills the
+ * PDR_OP_CLASSES-long arrays (milliseconds, algorithmic FLOPs of the tensor-core launches,
+ * launch counts) and stops profiling. */
+enum PdrOpClass { PDR_OP_CONV_TC = 0, PDR_OP_GN_STATS, PDR_OP_GN_APPLY, PDR_OP_RESAMPLE,
+                  PDR_OP_ATTENTION, PDR_OP_LINEAR, PDR_OP_STEM, PDR_OP_HEAD, PDR_OP_CLASSES };
+int pdr_unet_profile_begin(void* handle, int every, int max_forwards);
+int pdr_unet_profile_end(void* handle, double* ms, double* flops, long long* launches,
+                         long long* forwards);
+
 /* torch.randn-compatible standard normals (Philox4x32-10 + Box-Muller, torch's thread mapping):
  * out[numel] == torch.randn(numel, device='cuda') drawn with (seed, philox offset). */
 int pdr_randn_like_torch(float* out, long long numel, unsigned long long seed,

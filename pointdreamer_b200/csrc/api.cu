@@ -89,6 +89,14 @@ int pdr_unet_forward(void* handle, const float* x, const float* t, float* out, i
   return unet_forward(handle, x, t, out, n_out, (cudaStream_t)stream);
 }
 
+int pdr_unet_profile_begin(void* handle, int every, int max_forwards) {
+  return unet_profile_begin(handle, every, max_forwards);
+}
+int pdr_unet_profile_end(void* handle, double* ms, double* flops, long long* launches,
+                         long long* forwards) {
+  return unet_profile_end(handle, ms, flops, launches, forwards);
+}
+
 int pdr_randn_like_torch(float* out, long long numel, unsigned long long seed,
                          unsigned long long offset, void* stream) {
   PDR_CHECK_ARG(out && numel > 0, "pdr_randn_like_torch: bad argument");

@@ -94,12 +94,38 @@ class UnetEngine {
   int planned_B = 0;
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
-  std::vector<std::function<int(const float*, const float*, float*, int, cudaStream_t)>> ops;
+  using OpFn = std::function<int(const float*, const float*, float*, int, cudaStream_t)>;
+  struct Op {
+    OpFn fn;
+    int cls;       // PdrOpClass
+    double flops;  // algorithmic FLOPs of one launch (tensor-core convs only)
+  };
+  struct OpList {
+    std::vector<Op> v;
+    int cur_cls = 0;
+    double cur_flops = 0.0;
+    void push_back(OpFn f) { v.push_back(Op{std::move(f), cur_cls, cur_flops}); cur_flops = 0.0; }
+    void clear() { v.clear(); }
+  } ops;
+  // profiling: CUDA events around every op of sampled forwards
+  bool profiling = false;
+  int profile_every = 1, forward_counter = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_op;  // op index of each recorded (start, stop) pair
+  size_t ev_used = 0;
+  double prof_ms[PDR_OP_CLASSES] = {0}, prof_flops[PDR_OP_CLASSES] = {0};
+  long long prof_launches[PDR_OP_CLASSES] = {0};
+  long long prof_forwards = 0;
   std::vector<ConvOp*> conv_ops;
   std::string err;
 
-  ~UnetEngine() { clear_plan(); }
+  ~UnetEngine() {
+    clear_plan();
+    for (auto ev : ev_pool) cudaEventDestroy(ev);
+  }
   void clear_plan() {
+    ev_used = 0;
+    ev_op.clear();
     for (auto* c : conv_ops) delete c;
     conv_ops.clear();
     ops.clear();
@@ -167,6 +193,7 @@ class UnetEngine {
     const int HW = x1.H * x1.W, C1 = x1.C, C2 = x2 ? x2->C : 0, Bn = B_;
     float* ws = P<float>(off_gnws_);
     float* st = P<float>(off_stats_[which]);
+    ops.cur_cls = PDR_OP_GN_STATS;
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return gn_stats_launch(p1, p2, Bn, HW, C1, C2, ws, st, s);
     });
@@ -186,6 +213,7 @@ class UnetEngine {
     const __half* fl = film ? P<__half>(off_emb16_) : nullptr;
     const int fstride = emb_total_;
     __half* o = P<__half>(out.off);
+    ops.cur_cls = PDR_OP_GN_APPLY;
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return gn_apply_launch(p1, p2, Bn, H, W, C1, C2, st, g, b, fl, fstride, film_off,
                              silu ? 1 : 0, resample, o, s);
@@ -216,6 +244,8 @@ class UnetEngine {
     const __half* r = res ? P<__half>(res->off) : nullptr;
     __half* o = P<__half>(out.off);
     const bool has2 = x2 != nullptr;
+    ops.cur_cls = PDR_OP_CONV_TC;
+    ops.cur_flops = 2.0 * Bn * H * W * (double)Co * taps * (C1 + C2);
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return conv_tc_launch(&c->a1, has2 ? &c->a2 : nullptr, &c->w, bn, Bn, H, W, C1, C2, Co, taps,
                             bias, r, o, s);
@@ -248,6 +278,7 @@ class UnetEngine {
         const __half* src = P<__half>(x1.off);
         __half* dst = P<__half>(xr.off);
         const int H = x1.H, W = x1.W, Bn = B_;
+        ops.cur_cls = PDR_OP_RESAMPLE;
         ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
           return resample_launch(src, Bn, H, W, Cin, resample, dst, s);
         });
@@ -301,6 +332,8 @@ class UnetEngine {
       const __half* q = P<__half>(qkv.off);
       __half* o = P<__half>(a.off);
       const int T = x.H * x.W, Bn = B_;
+      ops.cur_cls = PDR_OP_ATTENTION;
+      ops.cur_flops = 4.0 * Bn * heads * (double)T * T * 64;
       ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
         return attention_launch(q, Bn, T, heads, o, s);
       });
@@ -383,6 +416,7 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
       float* emb = P<float>(off_emb_);
       __half* e16 = P<__half>(off_emb16_);
       const int etot = emb_total_;
+      ops.cur_cls = PDR_OP_LINEAR;
       ops.push_back([=](const float*, const float* t, float*, int, cudaStream_t s) {
         PDR_TRY(linear_launch(t, (const float*)w0->ptr, (const float*)b0->ptr, B, mc, ted, 2, e1,
                               nullptr, s));
@@ -405,6 +439,7 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
     if (!dry_) {
       __half* o = P<__half>(h.off);
       const int Cc = ch;
+      ops.cur_cls = PDR_OP_STEM;
       ops.push_back([=](const float* x, const float*, float*, int, cudaStream_t s) {
         return stem_conv_launch(x, (const __half*)w->ptr, (const float*)b->ptr, B, S, S, Cc, o, s);
       });
@@ -495,6 +530,7 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
       const __half* hp = P<__half>(h.off);
       const float* st = P<float>(off_stats_[0]);
       const int Cc = h.C;
+      ops.cur_cls = PDR_OP_HEAD;
       ops.push_back([=](const float*, const float*, float* out, int n_out, cudaStream_t s) {
         return head_launch(hp, st, (const float*)g->ptr, (const float*)b->ptr,
                            (const float*)w->ptr, (const float*)bb->ptr, B, S, S, Cc, n_out, out,
@@ -556,9 +592,70 @@ int unet_forward(void* handle, const float* x, const float* t, float* out, int n
   UnetEngine* e = (UnetEngine*)handle;
   PDR_CHECK_ARG(e->planned_B > 0, "unet_forward: call pdr_unet_plan first");
   PDR_CHECK_ARG(n_out >= 1 && n_out <= e->cfg.out_channels, "unet_forward: bad n_out");
-  for (auto& op : e->ops) PDR_TRY(op(x, t, out, n_out, stream));
+  const bool sample = e->profiling && (e->forward_counter++ % e->profile_every == 0) &&
+                      e->ev_used + 2 * e->ops.v.size() <= e->ev_pool.size();
+  if (!sample) {
+    for (auto& op : e->ops.v) PDR_TRY(op.fn(x, t, out, n_out, stream));
+    return 0;
+  }
+  for (size_t i = 0; i < e->ops.v.size(); ++i) {
+    PDR_CUDA(cudaEventRecord(e->ev_pool[e->ev_used], stream));
+    PDR_TRY(e->ops.v[i].fn(x, t, out, n_out, stream));
+    PDR_CUDA(cudaEventRecord(e->ev_pool[e->ev_used + 1], stream));
+    e->ev_op.push_back((int)i);
+    e->ev_used += 2;
+  }
+  e->prof_forwards++;
   return 0;
 }
+
+// Sampling profiler: time every op of each `every`-th forward with CUDA events on the launching
+// stream (bench.py's live roofline measurement).  max_forwards bounds the event pool.
+int unet_profile_begin(void* handle, int every, int max_forwards) {
+  PDR_CHECK_ARG(handle && every >= 1 && max_forwards >= 1, "unet_profile_begin: bad argument");
+  UnetEngine* e = (UnetEngine*)handle;
+  PDR_CHECK_ARG(e->planned_B > 0, "unet_profile_begin: plan first");
+  const size_t want = 2 * e->ops.v.size() * (size_t)max_forwards;
+  while (e->ev_pool.size() < want) {
+    cudaEvent_t ev;
+    PDR_CUDA(cudaEventCreate(&ev));
+    e->ev_pool.push_back(ev);
+  }
+  e->profiling = true;
+  e->profile_every = every;
+  e->forward_counter = 0;
+  e->ev_used = 0;
+  e->ev_op.clear();
+  e->prof_forwards = 0;
+  for (int c = 0; c < PDR_OP_CLASSES; ++c) e->prof_ms[c] = e->prof_flops[c] = 0, e->prof_launches[c] = 0;
+  return 0;
+}
+// Synchronises the events, accumulates per-class totals and stops profiling.
+int unet_profile_end(void* handle, double* ms, double* flops, long long* launches,
+                     long long* forwards) {
+  PDR_CHECK_ARG(handle && ms && flops && launches && forwards, "unet_profile_end: null argument");
+  UnetEngine* e = (UnetEngine*)handle;
+  for (size_t k = 0; k < e->ev_op.size(); ++k) {
+    PDR_CUDA(cudaEventSynchronize(e->ev_pool[2 * k + 1]));
+    float t = 0.f;
+    PDR_CUDA(cudaEventElapsedTime(&t, e->ev_pool[2 * k], e->ev_pool[2 * k + 1]));
+    const auto& op = e->ops.v[e->ev_op[k]];
+    e->prof_ms[op.cls] += t;
+    e->prof_flops[op.cls] += op.flops;
+    e->prof_launches[op.cls] += 1;
+  }
+  for (int c = 0; c < PDR_OP_CLASSES; ++c) {
+    ms[c] = e->prof_ms[c];
+    flops[c] = e->prof_flops[c];
+    launches[c] = e->prof_launches[c];
+  }
+  *forwards = e->prof_forwards;
+  e->profiling = false;
+  e->ev_used = 0;
+  e->ev_op.clear();
+  return 0;
+}
+
 // DDNM chain for V views at once (diffusion.py:459-570): prepare, `steps` x (U-Net + fused update),
 // final transform.  coef_host: [steps][7] floats (DdnmStepCoef order); t_dev: [steps][V] device.
 int ddnm_sample(void* handle, const float* sparse, const float* mask, int V, int steps,

@@ -18,6 +18,9 @@ int ddnm_sample(void* handle, const float* sparse, const float* mask, int V, int
                 const float* coef_host, const float* t_dev, unsigned long long seed,
                 unsigned long long offset_base, unsigned long long draws_per_chain, int chain0,
                 float* x, float* y, float* et, float* out, cudaStream_t stream);
+int unet_profile_begin(void* handle, int every, int max_forwards);
+int unet_profile_end(void* handle, double* ms, double* flops, long long* launches,
+                     long long* forwards);
 int unet_planned_batch(void* handle);
 int unet_image_size(void* handle);
 int unet_out_channels(void* handle);

@@ -1,0 +1,150 @@
+"""The drop-in boundary: `colorize_one_mesh` with the reference's signature (demo.py:38-253),
+plus `prepare`-style helpers to build its inputs from the reference's YAML configs.
+
+The path is project -> inpaint -> unproject.  What the reference runs AFTER the path inside the
+same function — `paint_invisible_areas_by_neighbors` (complete_unseen_by: neighbor),
+`paint_invisible_areas_by_optimize` and `optimize_color` (optimize_from) — are "next" rows
+ and are not built; they can be supplied as callables (`neighbor_fill=`,
+`optimize_color=`) — e.g. the reference's own functions — otherwise asking for them raises.
+"""
+import os
+
+import torch
+import yaml
+
+from . import camera as _camera
+from . import ours_utils as _ou
+from . import unproject as _un
+
+# keys of configs/*.yaml consumed on the path (SURVEY §5 "config")
+PATH_CONFIG_KEYS = ("view_num", "res", "cam_res", "refine_res", "point_validation_by_o3d",
+                    "refine_point_validation_by_remove_abnormal_depth",
+                    "hidden_point_removal_radius", "texture_gen_method", "point_size",
+                    "edge_point_size", "crop_img", "crop_padding", "mask_ratio_thresh",
+                    "optimize_from", "edge_dilate_kernels", "complete_unseen_by",
+                    "xatlas_texture_res")
+
+DEFAULT_CONFIG = dict(  # configs/default.yaml
+    camera_distribution="fibonacci_sphere", cam_res=512, view_num=8, res=256, point_size=1,
+    edge_point_size=1, point_validation_by_o3d=True, hidden_point_removal_radius=100,
+    refine_point_validation_by_remove_abnormal_depth=False, refine_res=512, crop_img=True,
+    crop_padding=0.05, mask_ratio_thresh=0.82, edge_dilate_kernels=[21], optimize_from="ours",
+    xatlas_texture_res=1024, complete_unseen_by="neighbor", texture_gen_method="DDNM_inpaint")
+
+
+def load_config(path):
+    """demo.py:315-316: YAML -> dict (the reference wraps it in a Munch and splats it as **cfg)."""
+    with open(path, "r") as f:
+        return yaml.safe_load(f)
+
+
+def prepare_cameras(cfg, device):
+    """demo.py:331-353: camera rig dict consumed by colorize_one_mesh."""
+    cams, base_dirs, eye_positions, up_dirs = _camera.create_cameras(
+        num_views=cfg["view_num"], distribution=cfg.get("camera_distribution", "fibonacci_sphere"),
+        distance=1.6, res=cfg["cam_res"], device=device)
+    return dict(cams=cams, base_dirs=base_dirs, eye_positions=eye_positions, up_dirs=up_dirs,
+                cam_RTs=None, cam_K=None)
+
+
+def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, camera_info,
+                      view_num, res, cam_res, refine_res, device, save_img_path,
+                      point_validation_by_o3d, refine_point_validation_by_remove_abnormal_depth,
+                      hidden_point_removal_radius, texture_gen_method, point_size, edge_point_size,
+                      crop_img, crop_padding, mask_ratio_thresh, optimize_from, edge_dilate_kernels,
+                      complete_unseen_by, inpainter, glctx, logger, xatlas_texture_res,
+                      neighbor_fill=None, optimize_color=None, **kwargs):
+    """demo.py:38-253.  Returns (vertices, uvs, faces, mesh_tex_idx, atlas_img[R,R,3], mask)."""
+    base_dirs = camera_info['base_dirs']
+    cams = camera_info['cams']
+    eye_positions = camera_info['eye_positions']
+    uvs = xatlas_dict['uvs']
+    mesh_tex_idx = xatlas_dict['mesh_tex_idx']
+    gb_pos = xatlas_dict['gb_pos']
+    mask = xatlas_dict['mask']
+    per_atlas_pixel_face_id = xatlas_dict['per_atlas_pixel_face_id']
+
+    with torch.no_grad():
+        # ---- PROJECT (demo.py:93-129)
+        (hard_masks, face_idxs, mesh_normalized_depths, vertice_uvs, uv_centers, uv_scales,
+         padding, point_uvs, point_depths) = _ou.get_rendered_hard_mask_and_face_idx_batch(
+            cams, vertices, faces, coords, glctx=glctx, rescale=crop_img, padding=crop_padding)
+        if cam_res != res:
+            hard_masks = _ou.resize_hard_masks(hard_masks, res)
+        point_validation, _ = _ou.get_point_validation_by_depth(
+            cam_res, point_uvs, point_depths, mesh_normalized_depths, offset=0.0001)
+        if point_validation_by_o3d:
+            point_validation2 = _ou.get_point_validation_by_o3d(coords, eye_positions,
+                                                                hidden_point_removal_radius)
+            point_validation = torch.logical_or(point_validation, point_validation2)
+        if refine_point_validation_by_remove_abnormal_depth:
+            raise NotImplementedError("refine_point_validation is off in every shipped config "
+                                      "(configs/default.yaml:46) and outside the hot path")
+        point_pixels = _ou.get_point_pixels(point_uvs, res)
+        sparse_imgs, hard_mask0s, hard_mask2s, inpaint_scale_factors = _ou.get_sparse_images(
+            point_pixels, colors, point_validation, hard_masks, save_img_path, view_num, res,
+            point_size, edge_point_size, mask_ratio_thresh)
+
+        # ---- INPAINT (demo.py:137-157), including the PNG cache of a previous run
+        inpainted_images = None
+        if save_img_path is not None:
+            from .io_utils import load_inpainted_pngs
+            cached = load_inpainted_pngs(save_img_path, view_num, res)
+            if cached is not None:
+                inpainted_images = torch.from_numpy(cached).to(device)
+        if inpainted_images is None:
+            inpainted_images = _ou.get_inpainted_images(
+                sparse_imgs, hard_mask0s, hard_mask2s, save_img_path, inpainter, view_num,
+                method=texture_gen_method)
+
+        # ---- UNPROJECT (demo.py:168-177)
+        complete_unseen_by_projection = (complete_unseen_by == 'unproject')
+        (atlas_img, shrinked_vis, point_view_ids, points_atlas_pixel_coord, points,
+         atlas_painted_mask) = _un.unproject(
+            inpainted_images, vertices, f_normals, res, cams, cam_res, base_dirs, gb_pos, mask,
+            per_atlas_pixel_face_id, uv_centers, uv_scales, padding, inpaint_scale_factors,
+            mesh_normalized_depths, edge_dilate_kernels, save_img_path,
+            complete_unseen_by_projection)
+
+        # ---- after the path (demo.py:180-246): "next" rows
+        if complete_unseen_by == 'unproject':
+            atlas_img = _un.dilate_atlas(atlas_img, mask)
+        elif complete_unseen_by == 'neighbor':
+            if neighbor_fill is None:
+                raise NotImplementedError(
+                    "complete_unseen_by='neighbor' (paint_invisible_areas_by_neighbors, "
+                    "unproject.py:93-196) is a 'next' row; pass neighbor_fill=<callable> or use "
+                    "complete_unseen_by='unproject' / None")
+            to_inpaint_face_id = per_atlas_pixel_face_id[0][torch.logical_not(atlas_painted_mask)].unique()
+            to_inpaint_face_id = to_inpaint_face_id[to_inpaint_face_id > -1]
+            atlas_img = neighbor_fill(vertices, faces, uvs, mesh_tex_idx, to_inpaint_face_id,
+                                      atlas_img, atlas_painted_mask, use_atlas=True)
+        elif complete_unseen_by == 'optimize':
+            raise NotImplementedError("complete_unseen_by='optimize' (TextureField) is out of scope")
+        if optimize_from is not None and optimize_from != 'None':
+            if optimize_color is None:
+                raise NotImplementedError(
+                    "optimize_from (optimize_color, ours_utils.py:1583-1785) is a 'next' row; pass "
+                    "optimize_color=<callable> or set optimize_from: None")
+            atlas_img = optimize_color(atlas_img, inpainted_images, shrinked_vis)
+    return vertices, uvs, faces, mesh_tex_idx, atlas_img, mask
+
+
+def colorize_from_host(scene, camera_info, cfg, inpainter, device):
+    """End-to-end convenience used by bench.py's `e2e` leg: every input starts in (pinned) HOST
+    memory, is copied to the device, run through colorize_one_mesh, and the atlas is copied back.
+    Returns (atlas_host [R,R,3] float32 pinned tensor, h2d_bytes, d2h_bytes)."""
+    xa = scene["xatlas_dict"]
+    host = [scene["xyz"], scene["rgb"], scene["vertices"], scene["faces"], scene["f_normals"],
+            xa["uvs"], xa["mesh_tex_idx"], xa["gb_pos"], xa["mask"], xa["per_atlas_pixel_face_id"]]
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d = [t.to(device, non_blocking=True) for t in host]
+    xad = dict(uvs=d[5], mesh_tex_idx=d[6], gb_pos=d[7], mask=d[8], per_atlas_pixel_face_id=d[9])
+    keys = {k: cfg[k] for k in PATH_CONFIG_KEYS}
+    out = colorize_one_mesh(d[0], d[1], d[2], d[3], d[4], xad, camera_info, device=device,
+                            save_img_path=None, inpainter=inpainter, glctx=None, logger=None, **keys)
+    atlas = out[4]
+    atlas_host = torch.empty(atlas.shape, dtype=atlas.dtype, pin_memory=True)
+    atlas_host.copy_(atlas, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return atlas_host, h2d, atlas.numel() * atlas.element_size()

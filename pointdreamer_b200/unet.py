@@ -282,3 +282,24 @@ def random_state_dict(cfg=None, seed=1234, device="cuda"):
                 gain = 0.3
             sd[name] = torch.randn(shape, generator=g, device=device) * (gain / fan_in ** 0.5)
     return sd
+
+
+OP_CLASSES = ("conv_tc", "gn_stats", "gn_apply", "resample", "attention", "linear", "stem", "head")
+
+
+def profile_begin(engine, every=10, max_forwards=16):
+    """Start sampling per-kernel-class CUDA-event timings of `engine` (see pdr_unet_profile_begin)."""
+    _lib.check(engine.lib.pdr_unet_profile_begin(engine.handle, int(every), int(max_forwards)),
+               "pdr_unet_profile_begin")
+
+
+def profile_end(engine):
+    """Stop sampling; returns {class: dict(ms, flops, launches)} and the number of sampled forwards."""
+    n = len(OP_CLASSES)
+    ms = (ctypes.c_double * n)()
+    fl = (ctypes.c_double * n)()
+    la = (ctypes.c_longlong * n)()
+    fw = ctypes.c_longlong(0)
+    _lib.check(engine.lib.pdr_unet_profile_end(engine.handle, ms, fl, la, ctypes.byref(fw)),
+               "pdr_unet_profile_end")
+    return {OP_CLASSES[i]: dict(ms=ms[i], flops=fl[i], launches=int(la[i])) for i in range(n)}, int(fw.value)
