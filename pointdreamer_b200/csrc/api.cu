@@ -29,7 +29,7 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
   }
   PDR_TRY(conv_tc_make_weight_map(&mw, w, Cout, taps * (C1 + C2), bn));
   return conv_tc_launch(&ma1, C2 > 0 ? &ma2 : nullptr, &mw, bn, B, H, W, C1, C2, Cout, taps, bias,
-                        (const __half*)residual, (__half*)out, (cudaStream_t)stream);
+                        (const __half*)residual, (__half*)out, nullptr, (cudaStream_t)stream);
 }
 
 int pdr_linear(const float* in, const float* W, const float* bias, int B, int K, int N,

@@ -39,6 +39,9 @@ struct ConvArgs {
   const float* bias;        // [Cout] or null
   const __half* residual;   // [B,H,W,Cout] or null
   __half* out;              // [B,H,W,Cout]
+  // optional fused GroupNorm statistics: per (m-tile, epilogue warp, 8-channel chunk) sum and
+  // sum of squares of the fp16 outputs, [tiles_m][4][Cout/8][2] floats (null = off)
+  float* stats_partial;
 };
 
 template <int BN, int STAGES>
@@ -204,6 +207,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
         uint32_t v[32];
+        float s8[4] = {0.f, 0.f, 0.f, 0.f}, q8[4] = {0.f, 0.f, 0.f, 0.f};
         tmem_ld_32x32(taddr + ch * 32, v);
         tmem_ld_wait();
         if (valid) {
@@ -234,6 +238,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint4* op = (uint4*)(args.out + row_off + ch * 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j) op[j] = ((const uint4*)o)[j];
+          if (args.stats_partial) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float s = 0.f, q2 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float f = __half2float(o[g * 8 + j]);
+                s += f;
+                q2 += f * f;
+              }
+              s8[g] = s;
+              q8[g] = q2;
+            }
+          }
+        }
+        if (args.stats_partial) {
+          // reduce the 8 per-row values (4 chunk sums, 4 chunk sums of squares) over the warp's 32
+          // rows with a halving butterfly (9 shuffles, fixed order -> deterministic): after the
+          // xor-16/8/4 steps every lane owns ONE of the 8 values, xor-2/1 finish it.
+          float w[8];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            w[g] = valid ? s8[g] : 0.f;
+            w[4 + g] = valid ? q8[g] : 0.f;
+          }
+          float x4[4], x2[2], x1;
+          {
+            const bool hi = lane & 16;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float send = hi ? w[i] : w[i + 4];
+              const float keep = hi ? w[i + 4] : w[i];
+              x4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+          }
+          {
+            const bool hi = lane & 8;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const float send = hi ? x4[i] : x4[i + 2];
+              const float keep = hi ? x4[i + 2] : x4[i];
+              x2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+          }
+          {
+            const bool hi = lane & 4;
+            const float send = hi ? x2[0] : x2[1];
+            const float keep = hi ? x2[1] : x2[0];
+            x1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          x1 += __shfl_xor_sync(0xffffffffu, x1, 2);
+          x1 += __shfl_xor_sync(0xffffffffu, x1, 1);
+          if ((lane & 3) == 0) {
+            const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            const int g = idx & 3, is_q = idx >> 2;
+            const int m_lin = tile / args.tiles_n;
+            args.stats_partial[(((size_t)m_lin * 4 + q) * (args.Cout / 8) + (n0 + ch * 32) / 8 + g) * 2 +
+                               is_q] = x1;
+          }
         }
       }
       tc_fence_before();
@@ -321,6 +384,13 @@ int conv_tc_make_weight_map(ConvTensorMap* out, const void* ptr, int Cout, int K
   return 0;
 }
 
+int conv_tc_stats_rows_per_image(int H, int W) {
+  int bw, bh, bb;
+  conv_tc_pick_box(1, H, W, &bw, &bh, &bb);
+  if (bb != 1 || bw * bh != 128 || W % bw || H % bh) return 0;
+  return (H / bh) * (W / bw) * 4;
+}
+
 int conv_tc_pick_bn(int B, int H, int W, int Cout) {
   // Largest N tile that divides Cout (fewer A re-reads); step down while SMs would sit idle.
   int bw, bh, bb;
@@ -359,7 +429,8 @@ static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const C
 
 int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
                    int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
-                   const float* bias, const __half* residual, __half* out, cudaStream_t stream) {
+                   const float* bias, const __half* residual, __half* out, float* stats_partial,
+                   cudaStream_t stream) {
   PDR_CHECK_ARG(taps == 9 || taps == 1, "taps must be 9 or 1 (got %d)", taps);
   PDR_CHECK_ARG(C1 > 0 && C1 % BLOCK_K == 0 && C2 % BLOCK_K == 0, "C1/C2 must be multiples of 64");
   PDR_CHECK_ARG(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256");
@@ -383,6 +454,9 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   args.bias = bias;
   args.residual = residual;
   args.out = out;
+  args.stats_partial = stats_partial;
+  PDR_CHECK_ARG(!stats_partial || (args.bb == 1 && Cout % 32 == 0),
+                "fused GroupNorm statistics need one image per tile (H*W >= 128)");
   if (BN == 256) return launch_impl<256, 4>(a1, a2, w, args, stream);
   if (BN == 128) return launch_impl<128, 6>(a1, a2, w, args, stream);
   return launch_impl<64, 8>(a1, a2, w, args, stream);

@@ -24,6 +24,10 @@ int conv_tc_make_weight_map(ConvTensorMap* out, const void* ptr, int Cout, int K
 // out[B,H,W,Cout] = conv(cat(A1,A2)) + bias (+ residual); taps = 9 (3x3 pad 1) or 1 (1x1)
 int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
                    int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
-                   const float* bias, const __half* residual, __half* out, cudaStream_t stream);
+                   const float* bias, const __half* residual, __half* out, float* stats_partial,
+                   cudaStream_t stream);
+// number of (m-tile, epilogue-warp) partial rows written per image when stats_partial is used,
+// or 0 when the fused statistics are not available for this spatial size
+int conv_tc_stats_rows_per_image(int H, int W);
 
 }  // namespace pdr

@@ -27,6 +27,8 @@ struct Act {  // NHWC fp16 activation in the arena
   size_t off = 0;
   int B = 0, H = 0, W = 0, C = 0;
   bool skip = false;  // owned by the skip stack
+  bool has_sums = false;  // per-8-channel GroupNorm sums were produced by the conv epilogue
+  size_t sums_off = 0;    // double[B][C/8][2]
   size_t bytes() const { return (size_t)B * H * W * C * 2; }
 };
 
@@ -163,6 +165,7 @@ class UnetEngine {
   bool dry_ = true;
   int B_ = 0;
   size_t off_stats_[2] = {0, 0}, off_gnws_ = 0, off_e1_ = 0, off_emb_ = 0, off_emb16_ = 0;
+  size_t off_partial_ = 0, partial_bytes_ = 0, partial_reserved_ = 0;
   int emb_total_ = 0;
   int emb_cursor_ = 0;
 
@@ -178,7 +181,9 @@ class UnetEngine {
     return a;
   }
   void drop(const Act& a) {
-    if (!a.skip) pl_.release(a.off);
+    if (a.skip) return;
+    pl_.release(a.off);
+    if (a.has_sums) pl_.release(a.sums_off);
   }
 
   int add_gn(const Act& x1, const Act* x2, const std::string& pname, int which,
@@ -194,6 +199,14 @@ class UnetEngine {
     float* ws = P<float>(off_gnws_);
     float* st = P<float>(off_stats_[which]);
     ops.cur_cls = PDR_OP_GN_STATS;
+    if (x1.has_sums && (!x2 || x2->has_sums) && (C1 + C2) % 256 == 0) {
+      const double* s1 = P<double>(x1.sums_off);
+      const double* s2 = x2 ? P<double>(x2->sums_off) : nullptr;
+      ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
+        return gn_finalize_sums_launch(s1, s2, Bn, HW, C1, C2, st, s);
+      });
+      return 0;
+    }
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return gn_stats_launch(p1, p2, Bn, HW, C1, C2, ws, st, s);
     });
@@ -221,8 +234,16 @@ class UnetEngine {
     return 0;
   }
 
+  // want_sums: also produce the GroupNorm sums of `out` in the epilogue (when the tile allows)
   int add_conv(const Act& x1, const Act* x2, const std::string& pname, int taps, const Act* res,
-               const Act& out) {
+               Act& out, bool want_sums = false) {
+    const int stat_rows = want_sums && out.C % 256 == 0 ? conv_tc_stats_rows_per_image(out.H, out.W) : 0;
+    if (stat_rows > 0) {
+      out.has_sums = true;
+      out.sums_off = pl_.alloc((size_t)B_ * (out.C / 8) * 2 * sizeof(double));
+      const size_t need = (size_t)B_ * stat_rows * (out.C / 8) * 2 * sizeof(float);
+      if (need > partial_bytes_) partial_bytes_ = need;
+    }
     const int Cin = x1.C + (x2 ? x2->C : 0);
     const Param* w = find(pname + ".weight", (size_t)out.C * taps * Cin * 2);
     const Param* b = find(pname + ".bias", (size_t)out.C * 4);
@@ -244,12 +265,20 @@ class UnetEngine {
     const __half* r = res ? P<__half>(res->off) : nullptr;
     __half* o = P<__half>(out.off);
     const bool has2 = x2 != nullptr;
+    float* partial = stat_rows > 0 ? P<float>(off_partial_) : nullptr;
     ops.cur_cls = PDR_OP_CONV_TC;
     ops.cur_flops = 2.0 * Bn * H * W * (double)Co * taps * (C1 + C2);
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return conv_tc_launch(&c->a1, has2 ? &c->a2 : nullptr, &c->w, bn, Bn, H, W, C1, C2, Co, taps,
-                            bias, r, o, s);
+                            bias, r, o, partial, s);
     });
+    if (stat_rows > 0) {
+      double* sums = P<double>(out.sums_off);
+      ops.cur_cls = PDR_OP_GN_STATS;
+      ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
+        return sums8_reduce_launch(partial, Bn, stat_rows, Co, sums, s);
+      });
+    }
     return 0;
   }
 
@@ -285,7 +314,7 @@ class UnetEngine {
       }
     }
     Act h1 = new_act(Ho, Wo, Cout);
-    PDR_TRY(add_conv(a1, nullptr, p + ".in_layers.2", 9, nullptr, h1));
+    PDR_TRY(add_conv(a1, nullptr, p + ".in_layers.2", 9, nullptr, h1, true));
     drop(a1);
     // out_layers: GN * (1+scale) + shift, SiLU, conv (+ skip)
     PDR_TRY(add_gn(h1, nullptr, p + ".out_layers.0", 1, nullptr));
@@ -305,7 +334,7 @@ class UnetEngine {
       skip = have_xr ? xr : x1;
     }
     Act out = new_act(Ho, Wo, Cout);
-    PDR_TRY(add_conv(a2, nullptr, p + ".out_layers.3", 9, &skip, out));
+    PDR_TRY(add_conv(a2, nullptr, p + ".out_layers.3", 9, &skip, out, true));
     drop(a2);
     if (skip_alloc) drop(skip);
     if (have_xr) drop(xr);
@@ -340,7 +369,7 @@ class UnetEngine {
     }
     drop(qkv);
     Act out = new_act(x.H, x.W, C);
-    PDR_TRY(add_conv(a, nullptr, p + ".proj_out", 1, &x, out));
+    PDR_TRY(add_conv(a, nullptr, p + ".proj_out", 1, &x, out, true));
     drop(a);
     *result = out;
     return 0;
@@ -398,6 +427,9 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
     }
     off_gnws_ = pl_.alloc((size_t)B * mx * 2 * 4096 * 4);
   }
+  // scratch of the conv epilogue's statistics rows (size known from the dry pass)
+  off_partial_ = pl_.alloc(partial_reserved_ > 0 ? partial_reserved_ : 1024);
+  partial_bytes_ = 0;
   off_e1_ = pl_.alloc((size_t)B * ted * 4);
   off_emb_ = pl_.alloc((size_t)B * ted * 4);
   off_emb16_ = pl_.alloc((size_t)B * emb_total_ * 2);
@@ -543,6 +575,16 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
     set_error("internal: emb_layers width mismatch (%d vs %d)", emb_cursor_, emb_total_);
     return -1;
   }
+  if (dry_) {
+    // the scratch was a placeholder in the dry pass: account for its real size
+    partial_reserved_ = (partial_bytes_ + 1023) & ~(size_t)1023;
+    if (need) *need = pl_.high_water() + partial_reserved_;
+    return 0;
+  }
+  if (partial_bytes_ > partial_reserved_) {
+    set_error("internal: statistics scratch grew between the dry and the real plan");
+    return -1;
+  }
   if (need) *need = pl_.high_water();
   if (!dry_) {
     if (pl_.high_water() > ws_bytes) {
@@ -584,6 +626,8 @@ int unet_workspace_bytes(void* handle, int B, size_t* bytes) {
 int unet_plan(void* handle, int B, void* workspace, size_t bytes) {
   PDR_CHECK_ARG(handle && workspace && B > 0, "unet_plan: bad argument");
   PDR_CHECK_ARG(((uintptr_t)workspace & 1023) == 0, "unet_plan: workspace must be 1 KiB aligned");
+  size_t need = 0;
+  PDR_TRY(((UnetEngine*)handle)->plan(B, nullptr, 0, true, &need));  // sizes the scratch
   return ((UnetEngine*)handle)->plan(B, workspace, bytes, false, nullptr);
 }
 int unet_forward(void* handle, const float* x, const float* t, float* out, int n_out,

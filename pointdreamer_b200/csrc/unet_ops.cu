@@ -13,6 +13,9 @@
 namespace pdr {
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// SiLU whose result is immediately rounded to fp16: ex2.approx / rcp.approx (abs error ~1e-6) is far
+// below the fp16 quantum, and the memory-bound GroupNorm pass stays memory-bound.
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float h2f(__half h) { return __half2float(h); }
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 
@@ -190,9 +193,28 @@ __global__ void gn_partial_kernel(const __half* __restrict__ x1, const __half* _
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   const int c0 = chunk * 8;
-  if (plane < planes) {
-    for (int p = p0 + plane; p < p1; p += planes) {
-      const uint4 v = __ldg((const uint4*)src_ptr(x1, x2, C1, C2, (size_t)b * HW + p, c0));
+  {
+    const __half* src = c0 < C1 ? x1 + c0 : x2 + (c0 - C1);
+    const size_t stride = c0 < C1 ? C1 : C2;
+    src += (size_t)b * HW * stride;
+    int p = p0 + plane;
+    for (; p + 3 * planes < p1; p += 4 * planes) {  // 4 independent 16-B loads in flight
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg((const uint4*)(src + (size_t)(p + u * planes) * stride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half* h = (const __half*)&v[u];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f = h2f(h[j]);
+          s[j] += f;
+          q[j] += f * f;
+        }
+      }
+    }
+    for (; p < p1; p += planes) {
+      const uint4 v = __ldg((const uint4*)(src + (size_t)p * stride));
       const __half* h = (const __half*)&v;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -277,6 +299,75 @@ int gn_stats_launch(const __half* x1, const __half* x2, int B, int HW, int C1, i
   return 0;
 }
 
+
+// ---- GroupNorm statistics fused into the producing conv (conv_tc epilogue) ----
+// reduce the epilogue's partial rows [B*R][C8][2] (fp32) to per-image per-8-channel sums
+// sums8[B][C8][2] (fp64), fixed summation order.
+__global__ void sums8_reduce_kernel(const float* __restrict__ partial, int R, int C8,
+                                    double* __restrict__ sums8) {
+  // grid (ceil(C8*2 / 32), B), block (32, PARTS): thread (col, part) sums a contiguous row range
+  constexpr int PARTS = 8;
+  __shared__ double sm[PARTS][32];
+  const int b = blockIdx.y;
+  const int col = blockIdx.x * 32 + threadIdx.x;  // index into [C8][2]
+  const int part = threadIdx.y;
+  const int per = (R + PARTS - 1) / PARTS;
+  const int r0 = part * per, r1 = min(R, r0 + per);
+  double acc = 0.0;
+  if (col < C8 * 2) {
+    const float* p = partial + ((size_t)b * R) * (C8 * 2) + col;
+    for (int r = r0; r < r1; ++r) acc += (double)p[(size_t)r * (C8 * 2)];
+  }
+  sm[part][threadIdx.x] = acc;
+  __syncthreads();
+  if (part == 0 && col < C8 * 2) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < PARTS; ++k) t += sm[k][threadIdx.x];
+    sums8[(size_t)b * C8 * 2 + col] = t;
+  }
+}
+
+int sums8_reduce_launch(const float* partial, int B, int R, int C, double* sums8,
+                        cudaStream_t stream) {
+  const int C8 = C / 8;
+  sums8_reduce_kernel<<<dim3(cdiv(C8 * 2, 32), B), dim3(32, 8), 0, stream>>>(partial, R, C8, sums8);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+// mean / rstd of GroupNorm32 over cat(x1, x2) from the per-8-channel sums of its sources
+__global__ void gn_finalize_sums_kernel(const double* __restrict__ s1, const double* __restrict__ s2,
+                                        int C1, int C2, int HW, float eps,
+                                        float* __restrict__ stats) {
+  const int b = blockIdx.x, g = threadIdx.x;  // 32 threads = 32 groups
+  const int C = C1 + C2, cpg = C / 32;
+  double s = 0.0, q = 0.0;
+  for (int c = g * cpg; c < (g + 1) * cpg; c += 8) {
+    const double* src = c < C1 ? s1 + ((size_t)b * (C1 / 8) + c / 8) * 2
+                               : s2 + ((size_t)b * (C2 / 8) + (c - C1) / 8) * 2;
+    s += src[0];
+    q += src[1];
+  }
+  const double cnt = (double)HW * cpg;
+  const double mean = s / cnt;
+  double var = q / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[((size_t)b * 32 + g) * 2 + 0] = (float)mean;
+  stats[((size_t)b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+int gn_finalize_sums_launch(const double* s1, const double* s2, int B, int HW, int C1, int C2,
+                            float* stats, cudaStream_t stream) {
+  PDR_CHECK_ARG((C1 + C2) % 256 == 0 && C1 % 8 == 0 && C2 % 8 == 0,
+                "fused GroupNorm statistics need 8-channel aligned groups");
+  gn_finalize_sums_kernel<<<B, 32, 0, stream>>>(s1, s2 ? s2 : s1, C1, C2, HW, 1e-5f, stats);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
 // apply: y = GN(x)*gamma+beta  [-> fp16] [ *(1+scale)+shift -> fp16 ] [ SiLU -> fp16 ]
 //        [ AvgPool2 / nearest-up2 ]  -> out NHWC fp16 [B,Ho,Wo,C]
 // resample: 0 none, 1 down (avg 2x2), 2 up (nearest 2x)
@@ -293,76 +384,117 @@ struct GnApplyArgs {
   __half* out;
 };
 
-__device__ __forceinline__ void gn_apply_8(const GnApplyArgs& a, int b, size_t pixel, int c0,
-                                           const float (&ga)[8], const float (&gb)[8],
-                                           const float (&fs)[8], const float (&fsh)[8],
-                                           float (&y)[8]) {
-  const uint4 v = __ldg((const uint4*)src_ptr(a.x1, a.x2, a.C1, a.C2, pixel, c0));
+// thread = fixed 8-channel chunk (affine constants live in registers), loops over pixels of its
+// block's slab with several 16-B loads in flight; grid = (pixel slabs, B)
+__device__ __forceinline__ void gn_transform_8(const uint4& v, const float (&ga)[8],
+                                               const float (&gb)[8], const float (&fs)[8],
+                                               const float (&fsh)[8], bool film, bool silu,
+                                               float (&y)[8]) {
   const __half* h = (const __half*)&v;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float t = round_h(h2f(h[j]) * ga[j] + gb[j]);      // GroupNorm32 output, fp16
-    if (a.film) t = round_h(round_h(t * fs[j]) + fsh[j]);  // h*(1+scale) -> fp16, +shift -> fp16
-    if (a.silu) t = round_h(silu_f(t));
+    float t = round_h(h2f(h[j]) * ga[j] + gb[j]);        // GroupNorm32 output, fp16
+    if (film) t = round_h(round_h(t * fs[j]) + fsh[j]);  // h*(1+scale) -> fp16, +shift -> fp16
+    if (silu) t = round_h(silu_fast(t));
     y[j] = t;
   }
-  (void)b;
+}
+__device__ __forceinline__ uint4 pack_8(const float (&y)[8]) {
+  __align__(16) __half o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(y[j]);
+  return *(const uint4*)o;
 }
 
-__global__ void gn_apply_kernel(const GnApplyArgs a) {
+template <int RESAMPLE>
+__global__ void gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
   const int C = a.C1 + a.C2;
   const int chunks = C / 8;
-  const int Ho = a.resample == 1 ? a.H / 2 : (a.resample == 2 ? a.H * 2 : a.H);
-  const int Wo = a.resample == 1 ? a.W / 2 : (a.resample == 2 ? a.W * 2 : a.W);
-  const size_t total = (size_t)a.B * Ho * Wo * chunks;
+  const int chunk = threadIdx.x % chunks, plane = threadIdx.x / chunks;
+  const int planes = blockDim.x / chunks;
+  const int b = blockIdx.y;
+  const int c0 = chunk * 8;
   const int cpg = C / 32;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int chunk = i % chunks;
-    const size_t po = i / chunks;
-    const int xo = po % Wo, yo = (po / Wo) % Ho, b = po / ((size_t)Wo * Ho);
-    const int c0 = chunk * 8;
-    float ga[8], gb[8], fs[8], fsh[8];
+  const bool film = a.film != nullptr, silu = a.silu != 0;
+  float ga[8], gb[8], fs[8], fsh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      const int g = c / cpg;
-      const float mean = a.stats[((size_t)b * 32 + g) * 2], rstd = a.stats[((size_t)b * 32 + g) * 2 + 1];
-      const float w = a.gamma[c];
-      ga[j] = rstd * w;
-      gb[j] = a.beta[c] - mean * ga[j];
-      if (a.film) {
-        const __half* f = a.film + (size_t)b * a.film_stride + a.film_off;
-        fs[j] = round_h(1.0f + h2f(f[c]));  // (1 + scale) in fp16
-        fsh[j] = h2f(f[C + c]);
-      } else {
-        fs[j] = 1.f, fsh[j] = 0.f;
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    const int g = c / cpg;
+    const float mean = a.stats[((size_t)b * 32 + g) * 2], rstd = a.stats[((size_t)b * 32 + g) * 2 + 1];
+    ga[j] = rstd * a.gamma[c];
+    gb[j] = a.beta[c] - mean * ga[j];
+    if (film) {
+      const __half* f = a.film + (size_t)b * a.film_stride + a.film_off;
+      fs[j] = round_h(1.0f + h2f(f[c]));  // (1 + scale) in fp16
+      fsh[j] = h2f(f[C + c]);
+    } else {
+      fs[j] = 1.f, fsh[j] = 0.f;
+    }
+  }
+  const __half* src = c0 < a.C1 ? a.x1 + c0 : a.x2 + (c0 - a.C1);
+  const size_t sstride = c0 < a.C1 ? a.C1 : a.C2;
+  const int H = a.H, W = a.W;
+  src += (size_t)b * H * W * sstride;
+  float y[8];
+  if (RESAMPLE == 0) {
+    __half* dst = a.out + (size_t)b * H * W * C + c0;
+    const int npix = H * W;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+    int p = p0 + plane;
+    for (; p + 3 * planes < p1; p += 4 * planes) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg((const uint4*)(src + (size_t)(p + u * planes) * sstride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        gn_transform_8(v[u], ga, gb, fs, fsh, film, silu, y);
+        *(uint4*)(dst + (size_t)(p + u * planes) * C) = pack_8(y);
       }
     }
-    float y[8];
-    if (a.resample == 1) {
+    for (; p < p1; p += planes) {
+      const uint4 v = __ldg((const uint4*)(src + (size_t)p * sstride));
+      gn_transform_8(v, ga, gb, fs, fsh, film, silu, y);
+      *(uint4*)(dst + (size_t)p * C) = pack_8(y);
+    }
+  } else if (RESAMPLE == 1) {  // AvgPool2d(2) of the activated tensor: loop over OUTPUT pixels
+    const int Ho = H / 2, Wo = W / 2;
+    __half* dst = a.out + (size_t)b * Ho * Wo * C + c0;
+    const int npix = Ho * Wo;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+    for (int p = p0 + plane; p < p1; p += planes) {
+      const int yo = p / Wo, xo = p - yo * Wo;
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = __ldg((const uint4*)(src + ((size_t)(2 * yo + (u >> 1)) * W + 2 * xo + (u & 1)) * sstride));
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      for (int dy = 0; dy < 2; ++dy)
-        for (int dx = 0; dx < 2; ++dx) {
-          const size_t pin = ((size_t)b * a.H + (2 * yo + dy)) * a.W + (2 * xo + dx);
-          gn_apply_8(a, b, pin, c0, ga, gb, fs, fsh, y);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += y[j];
-        }
+      for (int u = 0; u < 4; ++u) {
+        gn_transform_8(v[u], ga, gb, fs, fsh, film, silu, y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += y[j];
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) y[j] = acc[j] * 0.25f;
-    } else if (a.resample == 2) {
-      const size_t pin = ((size_t)b * a.H + (yo >> 1)) * a.W + (xo >> 1);
-      gn_apply_8(a, b, pin, c0, ga, gb, fs, fsh, y);
-    } else {
-      gn_apply_8(a, b, po, c0, ga, gb, fs, fsh, y);
+      *(uint4*)(dst + (size_t)p * C) = pack_8(y);
     }
-    __align__(16) __half o[8];
+  } else {  // nearest x2: loop over INPUT pixels, write the 2x2 block
+    const int Wo = W * 2;
+    __half* dst = a.out + (size_t)b * H * 2 * Wo * C + c0;
+    const int npix = H * W;
+    const int p0 = blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+    for (int p = p0 + plane; p < p1; p += planes) {
+      const int yi = p / W, xi = p - yi * W;
+      const uint4 v = __ldg((const uint4*)(src + (size_t)p * sstride));
+      gn_transform_8(v, ga, gb, fs, fsh, film, silu, y);
+      const uint4 o = pack_8(y);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(y[j]);
-    *(uint4*)(a.out + po * C + c0) = *(const uint4*)o;
+      for (int u = 0; u < 4; ++u)
+        *(uint4*)(dst + ((size_t)(2 * yi + (u >> 1)) * Wo + 2 * xi + (u & 1)) * C) = o;
+    }
   }
 }
 
@@ -380,12 +512,21 @@ int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int
   a.stats = stats, a.gamma = gamma, a.beta = beta;
   a.film = film, a.film_stride = film_stride, a.film_off = film_off;
   a.silu = silu, a.resample = resample, a.out = out;
-  const int Ho = resample == 1 ? H / 2 : (resample == 2 ? H * 2 : H);
-  const int Wo = resample == 1 ? W / 2 : (resample == 2 ? W * 2 : W);
-  long long total = (long long)B * Ho * Wo * (C / 8);
-  long long blocks = cdiv(total, 256);
-  if (blocks > 148 * 32) blocks = 148 * 32;
-  gn_apply_kernel<<<(int)blocks, 256, 0, stream>>>(a);
+  const int chunks = C / 8;
+  const int threads = chunks >= 256 ? chunks : 256 / chunks * chunks;
+  PDR_CHECK_ARG(threads <= 1024, "GroupNorm32 apply: too many channels");
+  const int planes = threads / chunks;
+  // pixels the kernel loops over: outputs for none/down, inputs for up
+  const int npix = resample == 1 ? (H / 2) * (W / 2) : H * W;
+  int ppb = planes * 32;  // ~32 pixels per thread
+  while (ppb > planes && (long long)cdiv(npix, ppb) * B < 148 * 4) ppb /= 2;
+  dim3 grid(cdiv(npix, ppb), B);
+  if (resample == 0)
+    gn_apply_kernel<0><<<grid, threads, 0, stream>>>(a, ppb);
+  else if (resample == 1)
+    gn_apply_kernel<1><<<grid, threads, 0, stream>>>(a, ppb);
+  else
+    gn_apply_kernel<2><<<grid, threads, 0, stream>>>(a, ppb);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;

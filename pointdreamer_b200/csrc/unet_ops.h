@@ -18,6 +18,12 @@ int gn_stats_slabs(int B, int HW);
 // ws_partial: float[B * slabs * 2 * (C1+C2)];  stats: float[B*32*2] (mean, rstd)
 int gn_stats_launch(const __half* x1, const __half* x2, int B, int HW, int C1, int C2,
                     float* ws_partial, float* stats, cudaStream_t stream);
+// statistics fused into the producing tcgen05 conv: partial rows -> per-8-channel fp64 sums ->
+// (mean, rstd) of a (possibly concatenated) tensor
+int sums8_reduce_launch(const float* partial, int B, int R, int C, double* sums8,
+                        cudaStream_t stream);
+int gn_finalize_sums_launch(const double* s1, const double* s2, int B, int HW, int C1, int C2,
+                            float* stats, cudaStream_t stream);
 int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int C1, int C2,
                     const float* stats, const float* gamma, const float* beta,
                     const __half* film, int film_stride, int film_off, int silu, int resample,

@@ -41,6 +41,32 @@ def test_engine_small_vs_reference_golden(cuda):
     assert np.array_equal(eng(x, t).cpu().numpy(), y)
 
 
+MEDIUM = dict(image_size=64, in_channels=3, model_channels=256, out_channels=6, num_res_blocks=1,
+              attention_resolutions="32", channel_mult=(1, 2), num_head_channels=64, num_heads=4,
+              use_scale_shift_norm=True, resblock_updown=True, use_fp16=True,
+              use_new_attention_order=False)
+
+
+def test_engine_medium_vs_oracle(cuda):
+    """Production-width channels (256/512): exercises BN=256 tiles, GroupNorm statistics fused
+    into the conv epilogue, concat GroupNorm from per-source sums."""
+    from pointdreamer_b200.unet import UNetEngine
+    sd = ounet.synthetic_state_dict(MEDIUM, seed=7)
+    eng = UNetEngine(sd, MEDIUM, device=cuda)
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 3, 64, 64, generator=gen)
+    t = torch.tensor([990.0, 250.0, 0.0])
+    y = eng(x.to(cuda), t.to(cuda)).cpu().numpy()
+    o16 = ounet.UNetOracle(sd, MEDIUM, emulate_fp16=True).forward(x, t).numpy()
+    o32 = ounet.UNetOracle(sd, MEDIUM, emulate_fp16=False).forward(x, t).numpy()
+    rel = np.linalg.norm(y - o16) / np.linalg.norm(o16)
+    print(f"medium: engine vs oracle16 max abs {np.abs(y - o16).max():.3e} rel L2 {rel:.3e}; "
+          f"engine vs oracle32 {np.abs(y - o32).max():.3e}; oracle16 vs oracle32 {np.abs(o16 - o32).max():.3e}")
+    assert rel < 2e-3 and np.abs(y - o16).max() < 1e-2
+    y1 = eng(x[1:2].to(cuda), t[1:2].to(cuda)).cpu().numpy()
+    assert np.array_equal(y1[0], y[1])  # batch-invariant bits
+
+
 def test_engine_batch_independence(cuda):
     """Chains are independent: a batch of 3 equals three batch-1 runs (fp16 exact)."""
     from pointdreamer_b200.unet import UNetEngine
