@@ -26,11 +26,9 @@ WORKLOAD = "30k-pt synthetic cloud, view_num=8, DDNM_inpaint 256^2 (T_sampling=1
 
 def path_config():
     from pointdreamer_b200 import demo
-    # configs/default.yaml with the two post-path "next" rows disabled and
-    # depth-only visibility (GPU hidden-point-removal is not built yet)
+    # configs/default.yaml with the two post-path "next" rows disabled
     return dict(demo.DEFAULT_CONFIG, view_num=V, res=RES, cam_res=CAM_RES,
-                xatlas_texture_res=ATLAS_RES, point_validation_by_o3d=False,
-                complete_unseen_by="unproject", optimize_from=None)
+                xatlas_texture_res=ATLAS_RES, complete_unseen_by="unproject", optimize_from=None)
 
 
 class ClockSampler:
@@ -320,7 +318,8 @@ def main():
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "shapes_per_step_per_gpu": 1,
                    "weights": "random-init ADM 256x256 architecture (552.8M params)",
-                   "point_validation_by_o3d": False, "complete_unseen_by": "unproject",
+                   "point_validation_by_o3d": cfg["point_validation_by_o3d"],
+                   "complete_unseen_by": "unproject",
                    "optimize_from": None, "edge_dilate_kernels": cfg["edge_dilate_kernels"],
                    "l2": "working set (1.9 GB U-Net arena per step) is far larger than the 126 MB L2"},
         "clocks": clocks,

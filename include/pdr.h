@@ -170,6 +170,17 @@ int pdr_point_visibility(const float* point_uvs, const float* point_depths,
                          int res, uint8_t* vis, long long* pix_cam, long long* pix_res,
                          void* stream);
 
+/* Hidden point removal for all views.  Replaces ours_utils.py:204-225 get_point_validation_by_o3d
+ * (open3d PointCloud.hidden_point_removal(eye, radius): spherical flip + float64 Qhull, visible =
+ * hull vertices).  Hull-vertex membership is decided per point by a 2-variable LP in fp64 after a
+ * projective map that sends the eye to infinity (see csrc/geom_hpr.cu).
+ *   points [N,3] fp32 ; frames [V,12] fp64 DEVICE = eye(3), ex(3), ey(3), ez(3) with ez the unit
+ *   vector from the eye towards the scene and (ex, ey, ez) orthonormal ; radius: the HPR radius
+ *   workspace: pdr_hidden_point_removal_workspace_bytes(V,N) bytes ; vis [V,N] u8 */
+size_t pdr_hidden_point_removal_workspace_bytes(int V, int N);
+int pdr_hidden_point_removal(const float* points, int N, int V, const double* frames,
+                             double radius, void* workspace, uint8_t* vis, void* stream);
+
 /* Sparse view images + hole masks.  Replaces ours_utils.py:848-882 get_sparse_images
  * (get_one_sparse_img 954-1044, paint_pixels 456-495, inner edge mask 497-532, kaolin
  * sided_distance 1013).

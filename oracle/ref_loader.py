@@ -256,14 +256,6 @@ def load(name):
 
 
 def hidden_point_removal_scipy(points, eye, radius):
-    """open3d PointCloud.hidden_point_removal(eye, radius) restated (Katz et al. HPR):
-    spherical flip p' = p - eye;  p^ = p' + 2 (R - |p'|) p'/|p'|;  append the origin;
-    visible = vertices of the convex hull (Qhull, float64) that are not the origin."""
-    from scipy.spatial import ConvexHull
-    p = np.asarray(points, dtype=np.float64) - np.asarray(eye, dtype=np.float64)[None]
-    n = np.linalg.norm(p, axis=1, keepdims=True)
-    flipped = p + 2.0 * (radius - n) * p / n
-    pts = np.concatenate([flipped, np.zeros((1, 3))], 0)
-    hull = ConvexHull(pts)
-    vid = np.unique(hull.vertices)
-    return vid[vid < points.shape[0]]
+    """open3d hidden_point_removal shim (see oracle/hpr.py)."""
+    from .hpr import hidden_point_removal
+    return hidden_point_removal(points, eye, radius)

@@ -223,6 +223,13 @@ int pdr_unproject(const float* images, int res, const float* cam_params, int V, 
                           workspace, atlas, shrinked_vis, point_view_ids, point_coords, points,
                           painted, (cudaStream_t)stream);
 }
+size_t pdr_hidden_point_removal_workspace_bytes(int V, int N) { return hpr_workspace_bytes(V, N); }
+int pdr_hidden_point_removal(const float* points, int N, int V, const double* frames,
+                             double radius, void* workspace, uint8_t* vis, void* stream) {
+  PDR_CHECK_ARG(points && frames && workspace && vis, "pdr_hidden_point_removal: null pointer");
+  PDR_CHECK_ARG(radius > 0.0, "pdr_hidden_point_removal: radius must be positive");
+  return hpr_launch(points, N, V, frames, radius, workspace, vis, (cudaStream_t)stream);
+}
 int pdr_mask_count(const uint8_t* mask, size_t n, int* ws_counter, int* out_host, void* stream) {
   PDR_CHECK_ARG(mask && ws_counter && out_host, "pdr_mask_count: null pointer");
   return mask_count_sync(mask, n, ws_counter, out_host, (cudaStream_t)stream);

@@ -45,6 +45,10 @@ int unproject_launch(const float* images, int res, const float* cams, int V, int
                      long long* point_coords, float* points, uint8_t* painted,
                      cudaStream_t stream);
 
+size_t hpr_workspace_bytes(int V, int N);
+int hpr_launch(const float* points, int N, int V, const double* frames_dev, double radius,
+               void* workspace, uint8_t* vis, cudaStream_t stream);
+
 int mask_count_sync(const uint8_t* mask, size_t n, int* ws_counter, int* out_host,
                     cudaStream_t stream);
 

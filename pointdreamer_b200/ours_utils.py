@@ -108,8 +108,7 @@ def get_point_pixels(point_uvs, res):
 
 
 def get_point_validation_by_o3d(points, eye_positions=None, hidden_point_removal_radius=None):
-    """ours_utils.py:204-225 (open3d hidden_point_removal).  GPU convex-hull HPR is not built
-    yet; there is deliberately no CPU fallback."""
+    """ours_utils.py:204-225 (open3d hidden_point_removal) -> bool[V,N], computed on the GPU."""
     from .hpr import hidden_point_removal
     return hidden_point_removal(points, eye_positions, hidden_point_removal_radius)
 
