@@ -84,7 +84,9 @@ typedef struct PdrUnetConfig {
  *   conv weights  fp16 [Cout][taps*Cin] (tap-major: K = (ky*3+kx)*Cin + c), biases fp32;
  *   GroupNorm / Linear / out.2 parameters fp32 in PyTorch layout;
  *   "emb_all.weight" [sum 2*Cout, 4*mc] / "emb_all.bias": every ResBlock's emb_layers.1
- *   concatenated in module order (input_blocks, middle_block, output_blocks). */
+ *   concatenated in module order (input_blocks, middle_block, output_blocks);
+ *   optional "input_blocks.0.0_tc.weight" fp16 [C][64] (the stem's [C][27] zero padded) +
+ *   "input_blocks.0.0_tc.bias": runs the stem as a tensor-core GEMM over 3x3 patches. */
 int pdr_unet_create(const PdrUnetConfig* cfg, void** handle);
 int pdr_unet_destroy(void* handle);
 int pdr_unet_set_param(void* handle, const char* name, const void* ptr, size_t bytes);

@@ -51,7 +51,8 @@ int pdr_group_norm(const void* x1, const void* x2, int B, int H, int W, int C1, 
   PDR_CHECK_ARG(x1 && gamma && beta && ws && stats && out, "pdr_group_norm: null pointer");
   PDR_TRY(gn_stats_launch((const __half*)x1, (const __half*)x2, B, H * W, C1, C2, ws, stats,
                           (cudaStream_t)stream));
-  return gn_apply_launch((const __half*)x1, (const __half*)x2, B, H, W, C1, C2, stats, gamma, beta,
+  return gn_apply_launch((const __half*)x1, (const __half*)x2, B, H, W, C1, C2, stats, nullptr,
+                         nullptr, gamma, beta,
                          (const __half*)film, film_stride, film_off, silu, resample, (__half*)out,
                          (cudaStream_t)stream);
 }

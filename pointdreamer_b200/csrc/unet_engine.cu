@@ -187,7 +187,7 @@ class UnetEngine {
   }
 
   int add_gn(const Act& x1, const Act* x2, const std::string& pname, int which,
-             const __half* /*unused*/) {
+             const __half* /*unused*/, bool for_head = false) {
     const int C = x1.C + (x2 ? x2->C : 0);
     const Param* g = find(pname + ".weight", (size_t)C * 4);
     const Param* b = find(pname + ".bias", (size_t)C * 4);
@@ -199,6 +199,8 @@ class UnetEngine {
     float* ws = P<float>(off_gnws_);
     float* st = P<float>(off_stats_[which]);
     ops.cur_cls = PDR_OP_GN_STATS;
+    if (!for_head && x1.has_sums && (!x2 || x2->has_sums) && (C1 + C2) % 256 == 0)
+      return 0;  // gn_apply derives mean/rstd from the conv epilogue's sums itself
     if (x1.has_sums && (!x2 || x2->has_sums) && (C1 + C2) % 256 == 0) {
       const double* s1 = P<double>(x1.sums_off);
       const double* s2 = x2 ? P<double>(x2->sums_off) : nullptr;
@@ -223,12 +225,15 @@ class UnetEngine {
     const __half* p2 = x2 ? P<__half>(x2->off) : nullptr;
     const int H = x1.H, W = x1.W, C1 = x1.C, C2 = x2 ? x2->C : 0, Bn = B_;
     const float* st = P<float>(off_stats_[which]);
+    const bool from_sums = x1.has_sums && (!x2 || x2->has_sums) && C % 256 == 0;
+    const double* s1 = from_sums ? P<double>(x1.sums_off) : nullptr;
+    const double* s2 = from_sums && x2 ? P<double>(x2->sums_off) : nullptr;
     const __half* fl = film ? P<__half>(off_emb16_) : nullptr;
     const int fstride = emb_total_;
     __half* o = P<__half>(out.off);
     ops.cur_cls = PDR_OP_GN_APPLY;
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
-      return gn_apply_launch(p1, p2, Bn, H, W, C1, C2, st, g, b, fl, fstride, film_off,
+      return gn_apply_launch(p1, p2, Bn, H, W, C1, C2, st, s1, s2, g, b, fl, fstride, film_off,
                              silu ? 1 : 0, resample, o, s);
     });
     return 0;
@@ -468,7 +473,20 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
     const Param* w = find("input_blocks.0.0.weight", (size_t)ch * 27 * 2);
     const Param* b = find("input_blocks.0.0.bias", (size_t)ch * 4);
     if (!w || !b) return -1;
-    if (!dry_) {
+    const bool tc_stem = params.count("input_blocks.0.0_tc.weight") && ch % 64 == 0;
+    if (tc_stem) {
+      // stem as a GEMM on the tensor cores: 27 -> 64 zero-padded patches, [ch][64] weights
+      Act patches = new_act(S, S, 64);
+      if (!dry_) {
+        __half* pp = P<__half>(patches.off);
+        ops.cur_cls = PDR_OP_STEM;
+        ops.push_back([=](const float* x, const float*, float*, int, cudaStream_t s) {
+          return stem_im2col_launch(x, B, S, S, pp, s);
+        });
+      }
+      PDR_TRY(add_conv(patches, nullptr, "input_blocks.0.0_tc", 1, nullptr, h, true));
+      drop(patches);
+    } else if (!dry_) {
       __half* o = P<__half>(h.off);
       const int Cc = ch;
       ops.cur_cls = PDR_OP_STEM;
@@ -552,7 +570,7 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
   }
   // ---- head ----
   {
-    PDR_TRY(add_gn(h, nullptr, "out.0", 0, nullptr));
+    PDR_TRY(add_gn(h, nullptr, "out.0", 0, nullptr, true));
     const Param* g = find("out.0.weight", (size_t)h.C * 4);
     const Param* b = find("out.0.bias", (size_t)h.C * 4);
     const Param* w = find("out.2.weight", (size_t)cfg.out_channels * h.C * 9 * 4);

@@ -169,6 +169,39 @@ int stem_conv_launch(const float* x, const __half* w, const float* bias, int B, 
   return 0;
 }
 
+// stem as a tensor-core GEMM: x [B,3,H,W] fp32 -> fp16 patches [B,H,W,64] (k = (ky*3+kx)*3 + c for
+// k < 27, zero above) consumed by conv_tc as a 1x1 conv with a [C][64] zero-padded weight
+__global__ void stem_im2col_kernel(const float* __restrict__ x, int B, int H, int W,
+                                   __half* __restrict__ out) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (size_t)B * H * W) return;
+  const int xw = p % W, yh = (p / W) % H, b = p / ((size_t)W * H);
+  __align__(16) __half v[64];
+#pragma unroll
+  for (int k = 27; k < 64; ++k) v[k] = __float2half_rn(0.f);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = yh + ky - 1, xx = xw + kx - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        v[(ky * 3 + kx) * 3 + c] =
+            __float2half_rn(ok ? __ldg(x + (((size_t)b * 3 + c) * H + yy) * W + xx) : 0.f);
+    }
+  uint4* o = (uint4*)(out + p * 64);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = ((const uint4*)v)[j];
+}
+
+int stem_im2col_launch(const float* x, int B, int H, int W, __half* out, cudaStream_t stream) {
+  stem_im2col_kernel<<<cdiv((long long)B * H * W, 128), 128, 0, stream>>>(x, B, H, W, out);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------ GroupNorm32 ----
 // statistics: per-(batch, slab, channel) partial sum / sum of squares in fp32, finalised in
 // double per (batch, group).  x = concat(x1[C1], x2[C2]) along channels, NHWC fp16.
@@ -375,7 +408,9 @@ struct GnApplyArgs {
   const __half* x1;
   const __half* x2;
   int C1, C2, B, H, W;
-  const float* stats;    // [B,32,2]
+  const float* stats;    // [B,32,2] (mean, rstd) or null when sums1/sums2 are given
+  const double* sums1;   // per-8-channel (sum, sumsq) of x1: double[B][C1/8][2]
+  const double* sums2;   // same for x2
   const float* gamma;    // [C]
   const float* beta;     // [C]
   const __half* film;    // [B, film_stride] fp16: scale at [coff + c], shift at [coff + C + c]
@@ -417,11 +452,31 @@ __global__ void gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
   const int cpg = C / 32;
   const bool film = a.film != nullptr, silu = a.silu != 0;
   float ga[8], gb[8], fs[8], fsh[8];
+  float mean8 = 0.f, rstd8 = 0.f;
+  if (a.sums1) {
+    // statistics straight from the conv epilogue's sums (cpg is a multiple of 8 here, so the
+    // thread's 8 channels share one group); same arithmetic as gn_finalize_sums_kernel
+    const int g = c0 / cpg;
+    double s = 0.0, q = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; c += 8) {
+      const double* src = c < a.C1 ? a.sums1 + ((size_t)b * (a.C1 / 8) + c / 8) * 2
+                                   : a.sums2 + ((size_t)b * (a.C2 / 8) + (c - a.C1) / 8) * 2;
+      s += src[0];
+      q += src[1];
+    }
+    const double cnt = (double)a.H * a.W * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    mean8 = (float)mean;
+    rstd8 = (float)(1.0 / sqrt(var + 1e-5));
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
     const int g = c / cpg;
-    const float mean = a.stats[((size_t)b * 32 + g) * 2], rstd = a.stats[((size_t)b * 32 + g) * 2 + 1];
+    const float mean = a.sums1 ? mean8 : a.stats[((size_t)b * 32 + g) * 2];
+    const float rstd = a.sums1 ? rstd8 : a.stats[((size_t)b * 32 + g) * 2 + 1];
     ga[j] = rstd * a.gamma[c];
     gb[j] = a.beta[c] - mean * ga[j];
     if (film) {
@@ -499,7 +554,8 @@ __global__ void gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
 }
 
 int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int C1, int C2,
-                    const float* stats, const float* gamma, const float* beta,
+                    const float* stats, const double* sums1, const double* sums2,
+                    const float* gamma, const float* beta,
                     const __half* film, int film_stride, int film_off, int silu, int resample,
                     __half* out, cudaStream_t stream) {
   const int C = C1 + C2;
@@ -510,6 +566,9 @@ int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int
   a.x2 = x2 ? x2 : x1;
   a.C1 = C1, a.C2 = C2, a.B = B, a.H = H, a.W = W;
   a.stats = stats, a.gamma = gamma, a.beta = beta;
+  a.sums1 = sums1, a.sums2 = sums2 ? sums2 : sums1;
+  PDR_CHECK_ARG(stats || sums1, "GroupNorm32 apply: no statistics given");
+  PDR_CHECK_ARG(!sums1 || (C % 256 == 0), "GroupNorm32 apply from sums needs 8-aligned groups");
   a.film = film, a.film_stride = film_stride, a.film_off = film_off;
   a.silu = silu, a.resample = resample, a.out = out;
   const int chunks = C / 8;

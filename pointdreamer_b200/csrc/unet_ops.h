@@ -14,6 +14,9 @@ int linear_launch(const float* in, const float* W, const float* bias, int B, int
 int stem_conv_launch(const float* x, const __half* w, const float* bias, int B, int H, int W,
                      int C, __half* out, cudaStream_t stream);
 
+// x [B,3,H,W] fp32 -> [B,H,W,64] fp16 3x3 patches (27 taps*channels, zero padded to 64)
+int stem_im2col_launch(const float* x, int B, int H, int W, __half* out, cudaStream_t stream);
+
 int gn_stats_slabs(int B, int HW);
 // ws_partial: float[B * slabs * 2 * (C1+C2)];  stats: float[B*32*2] (mean, rstd)
 int gn_stats_launch(const __half* x1, const __half* x2, int B, int HW, int C1, int C2,
@@ -25,7 +28,8 @@ int sums8_reduce_launch(const float* partial, int B, int R, int C, double* sums8
 int gn_finalize_sums_launch(const double* s1, const double* s2, int B, int HW, int C1, int C2,
                             float* stats, cudaStream_t stream);
 int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int C1, int C2,
-                    const float* stats, const float* gamma, const float* beta,
+                    const float* stats, const double* sums1, const double* sums2,
+                    const float* gamma, const float* beta,
                     const __half* film, int film_stride, int film_off, int silu, int resample,
                     __half* out, cudaStream_t stream);
 int resample_launch(const __half* x, int B, int H, int W, int C, int mode, __half* out,

@@ -143,6 +143,13 @@ class UNetEngine:
         for n in res_names:
             emb_w.append(sd[n + ".emb_layers.1.weight"].detach().to(dev).float())
             emb_b.append(sd[n + ".emb_layers.1.bias"].detach().to(dev).float())
+        # stem on the tensor cores: [C][27] -> zero-padded [C][64] (K index = (ky*3+kx)*3 + c)
+        stem = self._tensors["input_blocks.0.0.weight"]
+        if stem.shape[0] % 64 == 0:
+            w64 = torch.zeros(stem.shape[0], 64, dtype=torch.float16, device=dev)
+            w64[:, :27] = stem
+            self._set("input_blocks.0.0_tc.weight", w64)
+            self._set("input_blocks.0.0_tc.bias", self._tensors["input_blocks.0.0.bias"])
         self._set("emb_all.weight", torch.cat(emb_w, 0))
         self._set("emb_all.bias", torch.cat(emb_b, 0))
 
