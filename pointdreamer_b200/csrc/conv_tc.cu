@@ -399,10 +399,11 @@ int conv_tc_pick_bn(int B, int H, int W, int Cout) {
   int best = 0;
   for (int bn = 256; bn >= 64; bn >>= 1) {
     if (Cout % bn != 0) continue;
-    if (best == 0) best = bn;
+    best = bn;
     if (tiles_m * (Cout / bn) >= num_sms()) return bn;
-    best = bn;  // keep shrinking: more tiles for a layer that cannot fill the machine
-    if (bn == 128) break;  // BN=64 only when Cout demands it
+    // BN=64 halves the tensor-core efficiency of a tile: only worth it when even BN=128
+    // leaves more than half of the SMs idle (the 8x8 feature maps)
+    if (bn == 128 && tiles_m * (Cout / 128) * 2 > num_sms()) return 128;
   }
   return best;
 }

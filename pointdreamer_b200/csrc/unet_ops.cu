@@ -643,21 +643,24 @@ int resample_launch(const __half* x, int B, int H, int W, int C, int mode, __hal
 // Block = 8 rows x 32 cols of output pixels, thread = 4 consecutive pixels of a row;
 // channels are streamed through shared memory in chunks of HEAD_CC.
 static constexpr int HEAD_CC = 16;
-static constexpr int HEAD_TW = 32, HEAD_TH = 8;
+static constexpr int HEAD_TW = 32, HEAD_TH = 16;
+static constexpr int HEAD_THREADS = 128;  // 16 rows x 8 groups of 4 pixels
 
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(HEAD_THREADS)
 head_kernel(const __half* __restrict__ h, const float* __restrict__ stats,
             const float* __restrict__ gamma, const float* __restrict__ beta,
             const float* __restrict__ w, const float* __restrict__ bias, int B, int H, int W,
             int C, int n_out, float* __restrict__ out, int out_channels_total) {
   // w: [n_out_total(6)][C][3][3] fp32 (PyTorch layout); only the first n_out rows are used
-  __shared__ float s_act[(HEAD_TH + 2) * (HEAD_TW + 2) * HEAD_CC];
+  constexpr int PW = HEAD_TW + 2, PH = HEAD_TH + 2;
+  __shared__ float s_act[HEAD_CC * PH * PW];
   __shared__ float s_w[9 * HEAD_CC * 8];  // [tap][cc][8 padded outputs]
+  __shared__ float s_ab[2 * HEAD_CC];     // GroupNorm affine of the chunk's channels
   const int tiles_x = W / HEAD_TW, tiles_y = H / HEAD_TH;
   const int tile = blockIdx.x;
   const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
   const int x0 = tx * HEAD_TW, y0 = ty * HEAD_TH;
-  const int tid = threadIdx.x;  // 64 threads: 8 rows x 8 groups of 4 pixels
+  const int tid = threadIdx.x;
   const int row = tid / 8, col4 = (tid % 8) * 4;
   const int cpg = C / 32;
   float acc[4][6];
@@ -668,11 +671,24 @@ head_kernel(const __half* __restrict__ h, const float* __restrict__ stats,
 
   for (int cb = 0; cb < C; cb += HEAD_CC) {
     __syncthreads();
+    if (tid < HEAD_CC) {
+      const int c = cb + tid;
+      const int g = c / cpg;
+      const float mean = stats[((size_t)b * 32 + g) * 2], rstd = stats[((size_t)b * 32 + g) * 2 + 1];
+      const float a = rstd * gamma[c];
+      s_ab[tid] = a;
+      s_ab[HEAD_CC + tid] = beta[c] - mean * a;
+    }
+    for (int i = tid; i < 9 * HEAD_CC * 8; i += HEAD_THREADS) {
+      const int o = i % 8, cc = (i / 8) % HEAD_CC, tap = i / (8 * HEAD_CC);
+      s_w[i] = o < n_out ? w[((size_t)o * C + cb + cc) * 9 + tap] : 0.f;
+    }
+    __syncthreads();
     // stage normalised + SiLU activations (zero outside the image = conv zero padding)
-    for (int i = tid; i < (HEAD_TH + 2) * (HEAD_TW + 2) * (HEAD_CC / 8); i += blockDim.x) {
+    for (int i = tid; i < PH * PW * (HEAD_CC / 8); i += HEAD_THREADS) {
       const int c8 = i % (HEAD_CC / 8);
       const int pp = i / (HEAD_CC / 8);
-      const int px = pp % (HEAD_TW + 2), py = pp / (HEAD_TW + 2);
+      const int px = pp % PW, py = pp / PW;
       const int yy = y0 + py - 1, xx = x0 + px - 1;
       float v[8];
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
@@ -680,32 +696,23 @@ head_kernel(const __half* __restrict__ h, const float* __restrict__ stats,
             __ldg((const uint4*)(h + (((size_t)b * H + yy) * W + xx) * C + cb + c8 * 8));
         const __half* hh = (const __half*)&raw;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = cb + c8 * 8 + j;
-          const int g = c / cpg;
-          const float mean = stats[((size_t)b * 32 + g) * 2], rstd = stats[((size_t)b * 32 + g) * 2 + 1];
-          const float a = rstd * gamma[c];
-          v[j] = silu_f(h2f(hh[j]) * a + (beta[c] - mean * a));
-        }
+        for (int j = 0; j < 8; ++j)
+          v[j] = silu_f(h2f(hh[j]) * s_ab[c8 * 8 + j] + s_ab[HEAD_CC + c8 * 8 + j]);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s_act[(c8 * 8 + j) * (HEAD_TH + 2) * (HEAD_TW + 2) + pp] = v[j];
-    }
-    for (int i = tid; i < 9 * HEAD_CC * 8; i += blockDim.x) {
-      const int o = i % 8, cc = (i / 8) % HEAD_CC, tap = i / (8 * HEAD_CC);
-      s_w[i] = o < n_out ? w[((size_t)o * C + cb + cc) * 9 + tap] : 0.f;
+      for (int j = 0; j < 8; ++j) s_act[(c8 * 8 + j) * PH * PW + pp] = v[j];
     }
     __syncthreads();
     for (int cc = 0; cc < HEAD_CC; ++cc) {
-      const float* sa = s_act + cc * (HEAD_TH + 2) * (HEAD_TW + 2);
+      const float* sa = s_act + cc * PH * PW;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         float a6[6];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) a6[j] = sa[(row + ky) * (HEAD_TW + 2) + col4 + j];
+        for (int j = 0; j < 6; ++j) a6[j] = sa[(row + ky) * PW + col4 + j];
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const float4 w0 = *(const float4*)(s_w + ((ky * 3 + kx) * HEAD_CC + cc) * 8);
@@ -739,7 +746,7 @@ int head_launch(const __half* h, const float* stats, const float* gamma, const f
                 W, HEAD_TH, HEAD_TW);
   PDR_CHECK_ARG(C % HEAD_CC == 0 && C % 32 == 0 && n_out >= 1 && n_out <= 6, "head: bad channels");
   const int tiles = B * (H / HEAD_TH) * (W / HEAD_TW);
-  head_kernel<<<tiles, 64, 0, stream>>>(h, stats, gamma, beta, w, bias, B, H, W, C, n_out, out,
+  head_kernel<<<tiles, HEAD_THREADS, 0, stream>>>(h, stats, gamma, beta, w, bias, B, H, W, C, n_out, out,
                                         out_channels_total);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();

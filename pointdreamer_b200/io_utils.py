@@ -44,3 +44,36 @@ def load_inpainted_pngs(save_path, view_num, res):
         img = np.asarray(Image.open(p).convert("RGB"), dtype=np.float32) / 255.0
         out[i] = img.transpose(2, 0, 1)
     return out
+
+
+def read_ply_xyzrgb(path):
+    """utils/other_utils.py:155-162 without plyfile: the reference's demo clouds are binary
+    little-endian PLY with `x y z` float32 and `red green blue` uchar per vertex (15 B/vertex).
+    Returns (xyz float32 [N,3], rgb uint8 [N,3])."""
+    with open(path, "rb") as f:
+        header = b""
+        while not header.endswith(b"end_header\n"):
+            line = f.readline()
+            if not line:
+                raise ValueError(f"{path}: no end_header")
+            header += line
+        text = header.decode("ascii", "replace")
+        if "binary_little_endian" not in text:
+            raise NotImplementedError("only binary_little_endian PLY clouds are supported")
+        n = int([l for l in text.splitlines() if l.startswith("element vertex")][0].split()[-1])
+        props = [l.split()[1:] for l in text.splitlines() if l.startswith("property")]
+        dt = []
+        for typ, name in props:
+            dt.append((name, {"float": "<f4", "float32": "<f4", "uchar": "u1", "uint8": "u1",
+                              "double": "<f8", "int": "<i4"}[typ]))
+        data = np.frombuffer(f.read(n * np.dtype(dt).itemsize), dtype=np.dtype(dt), count=n)
+    xyz = np.stack([data["x"], data["y"], data["z"]], -1).astype(np.float32)
+    rgb = np.stack([data["red"], data["green"], data["blue"]], -1).astype(np.uint8)
+    return xyz, rgb
+
+
+def normalize_cloud(xyz):
+    """demo.py:377-380: centre on the bbox centre, divide by the largest bbox extent."""
+    vmin, vmax = xyz.min(0), xyz.max(0)
+    xyz = xyz - (vmax + vmin) / np.float32(2.0)
+    return (xyz / (vmax - vmin).max()).astype(np.float32)

@@ -30,8 +30,13 @@ def run_case(name, cfg):
     cu = ref_loader.load("utils.camera_utils")
     from torchvision.transforms import transforms
 
-    sc = synthetic.make_scene(cfg["n_points"], cfg["seed"], cfg["nu"], cfg["nv"],
-                              cfg["atlas_res"], charts=cfg["charts"])
+    if cfg.get("scene") == "clock":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from proxy_mesh import clock_scene
+        sc = clock_scene(os.path.join(HERE, "clock.ply"), atlas_res=cfg["atlas_res"])
+    else:
+        sc = synthetic.make_scene(cfg["n_points"], cfg["seed"], cfg["nu"], cfg["nv"],
+                                  cfg["atlas_res"], charts=cfg["charts"])
     dev = torch.device("cpu")
     V, res, cam_res = cfg["view_num"], cfg["res"], cfg["cam_res"]
     cams, base_dirs, eye_positions, up_dirs = cu.create_cameras(
@@ -66,6 +71,8 @@ def run_case(name, cfg):
         # HPR through the scipy/Qhull shim (ours_utils.py:204-225)
         pv2 = ou.get_point_validation_by_o3d(coords, eye_positions, 100)
         out["point_validation_o3d"] = pv2.numpy()
+        if cfg.get("use_o3d"):
+            pv = torch.logical_or(pv, pv2)  # demo.py:108-110
         # demo.py:121-125
         pp = (point_uvs * res).long()
         pp = torch.cat((pp[:, :, 1].unsqueeze(-1), pp[:, :, 0].unsqueeze(-1)), dim=-1)

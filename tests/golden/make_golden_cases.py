@@ -15,4 +15,10 @@ CASES = {
               res=64, cam_res=128, point_size=2, edge_point_size=2, crop_img=False,
               crop_padding=0.05, mask_ratio_thresh=0.82, edge_dilate_kernels=[7, 3],
               complete_unseen_by_projection=False),
+    # BASELINE.json configs[0]: dataset/demo_data/clock.ply, view_num=2, texture_gen_method='nearest'
+    # (configs/nearest.yaml), HPR on; proxy voxel-shell mesh + quad atlas (tests/proxy_mesh.py);
+    # reduced raster/atlas resolutions keep the fixture small
+    "clock": dict(scene="clock", view_num=2, res=128, cam_res=256, atlas_res=256, point_size=1,
+                  edge_point_size=1, crop_img=True, crop_padding=0.05, mask_ratio_thresh=0.82,
+                  edge_dilate_kernels=[21], complete_unseen_by_projection=True, use_o3d=True),
 }

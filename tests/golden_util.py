@@ -31,6 +31,10 @@ def load_geom_case(name):
     from make_golden_cases import CASES
     from pointdreamer_b200 import synthetic
     cfg = CASES[name]
-    sc = synthetic.make_scene(cfg["n_points"], cfg["seed"], cfg["nu"], cfg["nv"],
-                              cfg["atlas_res"], charts=cfg["charts"])
+    if cfg.get("scene") == "clock":
+        from proxy_mesh import clock_scene
+        sc = clock_scene(os.path.join(GOLDEN_DIR, "clock.ply"), atlas_res=cfg["atlas_res"])
+    else:
+        sc = synthetic.make_scene(cfg["n_points"], cfg["seed"], cfg["nu"], cfg["nv"],
+                                  cfg["atlas_res"], charts=cfg["charts"])
     return cfg, sc, load_npz(os.path.join(GOLDEN_DIR, f"geom_case_{name}.npz"))

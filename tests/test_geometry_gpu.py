@@ -34,6 +34,10 @@ def _run_pipeline(cfg, sc, dev, inpainted_override=None):
     out["hard_masks"] = hm
     pv, pix_cam = ours_utils.get_point_validation_by_depth(cam_res, puv, pdepth, depths, offset=0.0001)
     out.update(point_validation=pv, point_pixels_cam=pix_cam)
+    if cfg.get("use_o3d"):  # demo.py:108-110
+        pv2 = ours_utils.get_point_validation_by_o3d(coords, eyes, 100)
+        out["point_validation_o3d"] = pv2
+        pv = torch.logical_or(pv, pv2)
     pp = ours_utils.get_point_pixels(puv, res)
     out["point_pixels"] = pp
     sparse, m0, m2, scales = ours_utils.get_sparse_images(
@@ -57,10 +61,10 @@ def _run_pipeline(cfg, sc, dev, inpainted_override=None):
 EXACT = ["hard_masks_cam", "face_idxs", "mesh_depths", "vertice_uvs", "point_uvs", "point_depths",
          "uv_centers", "uv_scales", "hard_masks", "point_validation", "point_pixels_cam",
          "point_pixels", "sparse_imgs", "hard_mask0s", "hard_mask2s", "scale_factors",
-         "shrinked_vis", "points_atlas_pixel_coord", "atlas_points"]
+         "shrinked_vis", "points_atlas_pixel_coord", "atlas_points", "point_validation_o3d"]
 
 
-@pytest.mark.parametrize("name", ["a", "b", "c"])
+@pytest.mark.parametrize("name", ["a", "b", "c", "clock"])
 def test_geometry_vs_reference_golden(cuda, name):
     from oracle import fill as ofill
     cfg, sc, g = load_geom_case(name)

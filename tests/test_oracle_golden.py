@@ -10,7 +10,7 @@ from oracle import project as oproj
 from oracle import unproject as ounproj
 
 
-@pytest.fixture(scope="module", params=["a", "b", "c"])
+@pytest.fixture(scope="module", params=["a", "b", "c", "clock"])
 def case(request):
     return load_geom_case(request.param)
 
@@ -60,6 +60,11 @@ def test_visibility_and_sparse_images(case):
                                                g["mesh_depths"], offset=0.0001)
     assert np.array_equal(vis, g["point_validation"])
     assert np.array_equal(pix, g["point_pixels_cam"])
+    if cfg.get("use_o3d"):  # demo.py:108-110
+        from oracle import hpr as ohpr
+        vis2 = ohpr.point_validation_by_o3d(sc["xyz"], g["eye_positions"], 100)
+        assert np.array_equal(vis2, g["point_validation_o3d"])
+        vis = vis | vis2
     pp = oproj.point_pixels(g["point_uvs"], res)
     assert np.array_equal(pp, g["point_pixels"])
     sparse, m0, m2, scales = oproj.get_sparse_images(
