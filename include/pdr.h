@@ -38,7 +38,9 @@ unsigned long long pdr_launch_count(void);
  *   x1 [B,H,W,C1] fp16, x2 [B,H,W,C2] fp16 or NULL (channel concat, unet.py:660-662)
  *   w  [Cout][taps*(C1+C2)] fp16, K index = tap*(C1+C2)+c, tap = ky*3+kx
  *   bias [Cout] fp32 or NULL; residual [B,H,W,Cout] fp16 or NULL; out [B,H,W,Cout] fp16
- *   bn: N tile, 64 / 128 / 256 / 0 (auto), must divide Cout.  C1, C2, Cout % 64 == 0. */
+ *   bn: N tile, 64 / 128 / 256 (must divide Cout), 512 = 2-CTA kernel (cta_group::2, SM pairs share
+ *   the weight tile; needs Cout % 256 == 0 and an even number of 128-pixel tiles), 0 = auto.
+ *   C1, C2, Cout % 64 == 0. */
 int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias,
                 const void* residual, void* out, int B, int H, int W, int C1, int C2, int Cout,
                 int taps, int bn, void* stream);

@@ -27,7 +27,7 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
     PDR_CHECK_ARG(x2 != nullptr, "pdr_conv_tc: x2 is null but C2=%d", C2);
     PDR_TRY(conv_tc_make_act_map(&ma2, x2, B, H, W, C2));
   }
-  PDR_TRY(conv_tc_make_weight_map(&mw, w, Cout, taps * (C1 + C2), bn));
+  PDR_TRY(conv_tc_make_weight_map(&mw, w, Cout, taps * (C1 + C2), bn == 512 ? 128 : bn));
   return conv_tc_launch(&ma1, C2 > 0 ? &ma2 : nullptr, &mw, bn, B, H, W, C1, C2, Cout, taps, bias,
                         (const __half*)residual, (__half*)out, nullptr, (cudaStream_t)stream);
 }

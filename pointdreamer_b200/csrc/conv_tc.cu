@@ -54,6 +54,121 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
 };
 
+// One output tile of the epilogue for the calling warp (TMEM lane quadrant q): TMEM -> registers ->
+// +bias (+residual) -> fp16 -> global, plus the optional deterministic GroupNorm partial sums.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint32_t tmem_acc, int m_lin,
+                                              int n_tile, int q, int lane) {
+  const int r = q * 32 + lane;  // row of the tile == TMEM lane
+  const int pw = r % args.bw;
+  const int ph = (r / args.bw) % args.bh;
+  const int pb = r / (args.bw * args.bh);
+  int m_tile = m_lin;
+  const int tx = m_tile % args.tiles_x;
+  m_tile /= args.tiles_x;
+  const int ty = m_tile % args.tiles_y;
+  const int tb = m_tile / args.tiles_y;
+  const int x = tx * args.bw + pw, y = ty * args.bh + ph, b = tb * args.bb + pb;
+  const int n0 = n_tile * BN;
+  const bool valid = (b < args.B) && (y < args.H) && (x < args.W);
+  const size_t row_off = (((size_t)b * args.H + y) * args.W + x) * (size_t)args.Cout + n0;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+  for (int ch = 0; ch < BN / 32; ++ch) {
+    uint32_t v[32];
+    float s8[4] = {0.f, 0.f, 0.f, 0.f}, q8[4] = {0.f, 0.f, 0.f, 0.f};
+    tmem_ld_32x32(taddr + ch * 32, v);
+    tmem_ld_wait();
+    if (valid) {
+      const int nb = n0 + ch * 32;
+      __align__(16) __half o[32];
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (args.bias) bv = __ldg((const float4*)(args.bias + nb + j));
+        o[j + 0] = __float2half_rn(__uint_as_float(v[j + 0]) + bv.x);
+        o[j + 1] = __float2half_rn(__uint_as_float(v[j + 1]) + bv.y);
+        o[j + 2] = __float2half_rn(__uint_as_float(v[j + 2]) + bv.z);
+        o[j + 3] = __float2half_rn(__uint_as_float(v[j + 3]) + bv.w);
+      }
+      if (args.residual) {
+        // reference adds two fp16 tensors (unet.py:256, :305): fp32 add, one more rounding
+        const uint4* rp = (const uint4*)(args.residual + row_off + ch * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 rv = __ldg(rp + j);
+          const __half* rh = (const __half*)&rv;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            o[j * 8 + e] =
+                __float2half_rn(__half2float(o[j * 8 + e]) + __half2float(rh[e]));
+        }
+      }
+      uint4* op = (uint4*)(args.out + row_off + ch * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op[j] = ((const uint4*)o)[j];
+      if (args.stats_partial) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float s = 0.f, q2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float f = __half2float(o[g * 8 + j]);
+            s += f;
+            q2 += f * f;
+          }
+          s8[g] = s;
+          q8[g] = q2;
+        }
+      }
+    }
+    if (args.stats_partial) {
+      // reduce the 8 per-row values (4 chunk sums, 4 chunk sums of squares) over the warp's 32
+      // rows with a halving butterfly (9 shuffles, fixed order -> deterministic): after the
+      // xor-16/8/4 steps every lane owns ONE of the 8 values, xor-2/1 finish it.
+      float w[8];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        w[g] = valid ? s8[g] : 0.f;
+        w[4 + g] = valid ? q8[g] : 0.f;
+      }
+      float x4[4], x2[2], x1;
+      {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = hi ? w[i] : w[i + 4];
+          const float keep = hi ? w[i + 4] : w[i];
+          x4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float send = hi ? x4[i] : x4[i + 2];
+          const float keep = hi ? x4[i + 2] : x4[i];
+          x2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      {
+        const bool hi = lane & 4;
+        const float send = hi ? x2[0] : x2[1];
+        const float keep = hi ? x2[1] : x2[0];
+        x1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      x1 += __shfl_xor_sync(0xffffffffu, x1, 2);
+      x1 += __shfl_xor_sync(0xffffffffu, x1, 1);
+      if ((lane & 3) == 0) {
+        const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        const int g = idx & 3, is_q = idx >> 2;
+                    args.stats_partial[(((size_t)m_lin * 4 + q) * (args.Cout / 8) + (n0 + ch * 32) / 8 + g) * 2 +
+                           is_q] = x1;
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -183,122 +298,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   } else if (warp >= 4) {
     // ========================================================= epilogue ====
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int r = q * 32 + lane;  // row of the tile == TMEM lane
-    const int pw = r % args.bw;
-    const int ph = (r / args.bw) % args.bh;
-    const int pb = r / (args.bw * args.bh);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_tile = tile % args.tiles_n;
-      int m_tile = tile / args.tiles_n;
-      const int tx = m_tile % args.tiles_x;
-      m_tile /= args.tiles_x;
-      const int ty = m_tile % args.tiles_y;
-      const int tb = m_tile / args.tiles_y;
-      const int x = tx * args.bw + pw, y = ty * args.bh + ph, b = tb * args.bb + pb;
-      const int n0 = n_tile * BN;
-      const bool valid = (b < args.B) && (y < args.H) && (x < args.W);
-      const size_t row_off = (((size_t)b * args.H + y) * args.W + x) * (size_t)args.Cout + n0;
-
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t v[32];
-        float s8[4] = {0.f, 0.f, 0.f, 0.f}, q8[4] = {0.f, 0.f, 0.f, 0.f};
-        tmem_ld_32x32(taddr + ch * 32, v);
-        tmem_ld_wait();
-        if (valid) {
-          const int nb = n0 + ch * 32;
-          __align__(16) __half o[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (args.bias) bv = __ldg((const float4*)(args.bias + nb + j));
-            o[j + 0] = __float2half_rn(__uint_as_float(v[j + 0]) + bv.x);
-            o[j + 1] = __float2half_rn(__uint_as_float(v[j + 1]) + bv.y);
-            o[j + 2] = __float2half_rn(__uint_as_float(v[j + 2]) + bv.z);
-            o[j + 3] = __float2half_rn(__uint_as_float(v[j + 3]) + bv.w);
-          }
-          if (args.residual) {
-            // reference adds two fp16 tensors (unet.py:256, :305): fp32 add, one more rounding
-            const uint4* rp = (const uint4*)(args.residual + row_off + ch * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 rv = __ldg(rp + j);
-              const __half* rh = (const __half*)&rv;
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                o[j * 8 + e] =
-                    __float2half_rn(__half2float(o[j * 8 + e]) + __half2float(rh[e]));
-            }
-          }
-          uint4* op = (uint4*)(args.out + row_off + ch * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) op[j] = ((const uint4*)o)[j];
-          if (args.stats_partial) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float s = 0.f, q2 = 0.f;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float f = __half2float(o[g * 8 + j]);
-                s += f;
-                q2 += f * f;
-              }
-              s8[g] = s;
-              q8[g] = q2;
-            }
-          }
-        }
-        if (args.stats_partial) {
-          // reduce the 8 per-row values (4 chunk sums, 4 chunk sums of squares) over the warp's 32
-          // rows with a halving butterfly (9 shuffles, fixed order -> deterministic): after the
-          // xor-16/8/4 steps every lane owns ONE of the 8 values, xor-2/1 finish it.
-          float w[8];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            w[g] = valid ? s8[g] : 0.f;
-            w[4 + g] = valid ? q8[g] : 0.f;
-          }
-          float x4[4], x2[2], x1;
-          {
-            const bool hi = lane & 16;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float send = hi ? w[i] : w[i + 4];
-              const float keep = hi ? w[i + 4] : w[i];
-              x4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-          }
-          {
-            const bool hi = lane & 8;
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const float send = hi ? x4[i] : x4[i + 2];
-              const float keep = hi ? x4[i + 2] : x4[i];
-              x2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-          }
-          {
-            const bool hi = lane & 4;
-            const float send = hi ? x2[0] : x2[1];
-            const float keep = hi ? x2[1] : x2[0];
-            x1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-          }
-          x1 += __shfl_xor_sync(0xffffffffu, x1, 2);
-          x1 += __shfl_xor_sync(0xffffffffu, x1, 1);
-          if ((lane & 3) == 0) {
-            const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-            const int g = idx & 3, is_q = idx >> 2;
-            const int m_lin = tile / args.tiles_n;
-            args.stats_partial[(((size_t)m_lin * 4 + q) * (args.Cout / 8) + (n0 + ch * 32) / 8 + g) * 2 +
-                               is_q] = x1;
-          }
-        }
-      }
+      epilogue_tile<BN>(args, tmem_base + (uint32_t)(acc * BN), tile / args.tiles_n,
+                        tile % args.tiles_n, q, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -314,6 +320,181 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a cluster of two CTAs (one SM pair) computes a 256 x 256 output
+// tile.  Each CTA stages its own 128-row A tile and HALF of the 256-row weight tile; the leader's
+// tcgen05.mma reads both halves, so shared-memory traffic per FLOP drops by a third and each SM's
+// TMEM holds its own 128 x 256 accumulator.  Only the leader CTA issues MMAs; both run TMA
+// producers and epilogues.
+template <int STAGES>
+struct SmemLayout2 {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = 128 * BLOCK_K * 2;  // this CTA's half of the 256-row B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const ConvArgs args) {
+  constexpr int BN = 256;
+  using L = SmemLayout2<STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int Ctot = args.C1 + args.C2;
+  const int kchunks_per_tap = Ctot / BLOCK_K;
+  const int num_k = args.taps * kchunks_per_tap;
+  const int tiles_m = args.tiles_b * args.tiles_y * args.tiles_x;  // even (checked on the host)
+  const int num_pairs = (tiles_m / 2) * args.tiles_n;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    if (args.C2 > 0) tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      // leader only: its arrive.expect_tx covers the bytes of BOTH CTAs.  The peer never runs a
+      // phase ahead (its slots are released by the leader's multicast commit), so its TMA bytes
+      // can only land in the phase the leader is about to arm.
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);  // multicast tcgen05.commit of the leader
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);   // multicast tcgen05.commit
+      mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps of each CTA (used in the leader only)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc2(tmem_ptr_smem, 2 * BN);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ============================================ TMA producer (both CTAs) ====
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pair = cluster_id; pair < num_pairs; pair += num_clusters) {
+        const int n_tile = pair % args.tiles_n;
+        int m_tile = (pair / args.tiles_n) * 2 + (int)rank;
+        const int tx = m_tile % args.tiles_x;
+        m_tile /= args.tiles_x;
+        const int ty = m_tile % args.tiles_y;
+        const int tb = m_tile / args.tiles_y;
+        const int x0 = tx * args.bw, y0 = ty * args.bh, b0 = tb * args.bb;
+        const int n0 = n_tile * BN + (int)rank * 128;  // this CTA's half of the weight rows
+        for (int k = 0; k < num_k; ++k) {
+          const int tap = k / kchunks_per_tap;
+          const int kc = k - tap * kchunks_per_tap;
+          int dy = 0, dx = 0;
+          if (args.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);  // bytes of both CTAs
+          const int c = kc * BLOCK_K;
+          if (c < args.C1)
+            tma2_load_4d(sa, &tmA1, &full_bar[stage], c, x0 + dx, y0 + dy, b0);
+          else
+            tma2_load_4d(sa, &tmA2, &full_bar[stage], c - args.C1, x0 + dx, y0 + dy, b0);
+          tma2_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 && leader) {
+    // ================================================ MMA issuer (leader) ====
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int pair = cluster_id; pair < num_pairs; pair += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int k = 0; k < num_k; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + kk * UMMA_K * 2);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + kk * UMMA_K * 2);
+            umma2_f16(tmem_d, adesc, bdesc, idesc, (k | kk) != 0 ? 1u : 0u);
+          }
+          umma2_commit_multicast(&empty_bar[stage]);  // frees the slot in both CTAs
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma2_commit_multicast(&tmem_full[acc]);  // both CTAs' epilogues
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ============================================== epilogue (both CTAs) ====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int pair = cluster_id; pair < num_pairs; pair += num_clusters) {
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN>(args, tmem_base + (uint32_t)(acc * BN),
+                        (pair / args.tiles_n) * 2 + (int)rank, pair % args.tiles_n, q, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's barrier
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody may exit (or free TMEM) while the peer still uses its smem/TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 2 * BN);
   }
 }
 
@@ -392,10 +573,15 @@ int conv_tc_stats_rows_per_image(int H, int W) {
 }
 
 int conv_tc_pick_bn(int B, int H, int W, int Cout) {
-  // Largest N tile that divides Cout (fewer A re-reads); step down while SMs would sit idle.
+  // Returns the N tile: 512 = the 2-CTA kernel (256-wide tile per SM pair), else the largest
+  // 1-CTA tile that divides Cout, stepping down while SMs would sit idle.
   int bw, bh, bb;
   conv_tc_pick_box(B, H, W, &bw, &bh, &bb);
   const long long tiles_m = (long long)cdiv(B, bb) * (H / bh) * (W / bw);
+  // SM pairs sharing the weight tile win once there are >= 4 waves of 256x256 tiles (measured:
+  // 1436 vs 1255 TFLOP/s on the 256->256 3x3 layer at 256^2; smaller layers lose to quantisation)
+  if (Cout % 256 == 0 && tiles_m % 2 == 0 && (tiles_m / 2) * (Cout / 256) >= 4 * (num_sms() / 2))
+    return 512;
   int best = 0;
   for (int bn = 256; bn >= 64; bn >>= 1) {
     if (Cout % bn != 0) continue;
@@ -428,13 +614,37 @@ static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const C
   return 0;
 }
 
+template <int STAGES>
+static int launch_impl2(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
+                        const ConvArgs& args, cudaStream_t stream) {
+  using L = SmemLayout2<STAGES>;
+  constexpr int smem_bytes = L::TOTAL + 1024;
+  static bool configured = false;
+  if (!configured) {
+    PDR_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<STAGES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    configured = true;
+  }
+  const int pairs = (args.tiles_b * args.tiles_y * args.tiles_x / 2) * args.tiles_n;
+  int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
+  conv_tc2_kernel<STAGES><<<2 * clusters, NUM_THREADS, smem_bytes, stream>>>(
+      *(const CUtensorMap*)a1, *(const CUtensorMap*)(a2 ? a2 : a1), *(const CUtensorMap*)w, args);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+// BN == 512 selects the 2-CTA kernel (256-wide N tile per SM pair; the weight map must have been
+// encoded with a 128-row box)
 int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
                    int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
                    cudaStream_t stream) {
   PDR_CHECK_ARG(taps == 9 || taps == 1, "taps must be 9 or 1 (got %d)", taps);
   PDR_CHECK_ARG(C1 > 0 && C1 % BLOCK_K == 0 && C2 % BLOCK_K == 0, "C1/C2 must be multiples of 64");
-  PDR_CHECK_ARG(BN == 64 || BN == 128 || BN == 256, "BN must be 64, 128 or 256");
+  PDR_CHECK_ARG(BN == 64 || BN == 128 || BN == 256 || BN == 512, "BN must be 64, 128, 256 or 512");
+  const bool two_cta = BN == 512;
+  if (two_cta) BN = 256;
   PDR_CHECK_ARG(Cout % BN == 0, "Cout (%d) must be a multiple of BN (%d)", Cout, BN);
   PDR_CHECK_ARG(C2 == 0 || a2 != nullptr, "second A tensor map missing");
   ConvArgs args;
@@ -458,6 +668,11 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   args.stats_partial = stats_partial;
   PDR_CHECK_ARG(!stats_partial || (args.bb == 1 && Cout % 32 == 0),
                 "fused GroupNorm statistics need one image per tile (H*W >= 128)");
+  if (two_cta) {
+    PDR_CHECK_ARG((args.tiles_b * args.tiles_y * args.tiles_x) % 2 == 0,
+                  "2-CTA conv needs an even number of 128-pixel tiles");
+    return launch_impl2<6>(a1, a2, w, args, stream);
+  }
   if (BN == 256) return launch_impl<256, 4>(a1, a2, w, args, stream);
   if (BN == 128) return launch_impl<128, 6>(a1, a2, w, args, stream);
   return launch_impl<64, 8>(a1, a2, w, args, stream);

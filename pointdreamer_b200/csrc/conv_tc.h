@@ -13,7 +13,8 @@ struct alignas(64) ConvTensorMap {
 
 // 128-output-pixel tile of an H x W feature map: bw*bh*bb == 128
 void conv_tc_pick_box(int B, int H, int W, int* bw, int* bh, int* bb);
-// N tile (128 or 256) that keeps all SMs busy for this layer
+// N tile that keeps all SMs busy for this layer: 64 / 128 / 256, or 512 = the 2-CTA kernel
+// (cta_group::2, 256-wide tile per SM pair; its weight map uses a 128-row box)
 int conv_tc_pick_bn(int B, int H, int W, int Cout);
 
 // NHWC fp16 activation [B,H,W,C], C % 64 == 0

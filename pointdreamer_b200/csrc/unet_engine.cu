@@ -264,7 +264,7 @@ class UnetEngine {
     const int bn = conv_tc_pick_bn(B_, out.H, out.W, out.C);
     PDR_TRY(conv_tc_make_act_map(&c->a1, P<__half>(x1.off), B_, x1.H, x1.W, x1.C));
     if (x2) PDR_TRY(conv_tc_make_act_map(&c->a2, P<__half>(x2->off), B_, x2->H, x2->W, x2->C));
-    PDR_TRY(conv_tc_make_weight_map(&c->w, w->ptr, out.C, taps * Cin, bn));
+    PDR_TRY(conv_tc_make_weight_map(&c->w, w->ptr, out.C, taps * Cin, bn == 512 ? 128 : bn));
     const int H = out.H, W = out.W, C1 = x1.C, C2 = x2 ? x2->C : 0, Co = out.C, Bn = B_;
     const float* bias = (const float*)b->ptr;
     const __half* r = res ? P<__half>(res->off) : nullptr;

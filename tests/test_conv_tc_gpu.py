@@ -69,3 +69,19 @@ def test_conv_many_tiles_persistent(cuda):
     assert err <= 4e-3 * max(scale, 1.0)
     err, scale = _run(cuda, 2, 128, 128, 128, 0, 128, 9, 128)
     assert err <= 4e-3 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 16, 16, 64, 0, 256, 9),      # 4 m-tiles -> 2 pairs, single K segment
+    (2, 32, 32, 128, 64, 512, 9),    # two sources, 2 n-tiles
+    (1, 64, 64, 256, 0, 256, 9),
+    (4, 128, 128, 64, 0, 256, 9),    # many pairs per cluster: ring wrap + TMEM double buffering
+    (8, 8, 8, 128, 0, 256, 1),       # bb = 2
+])
+def test_conv_two_cta(cuda, shape):
+    """cta_group::2 variant (bn=512 selects it): SM pairs share the weight tile."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W, C1, C2, Cout, taps = shape
+    err, scale = _run(cuda, B, H, W, C1, C2, Cout, taps, 512, residual=True)
+    assert err <= 4e-3 * max(scale, 1.0)

@@ -20,7 +20,7 @@ shapes = [  # B,H,W,C1,C2,Cout,taps
 ]
 res = []
 for (B, H, W, C1, C2, Cout, taps) in shapes:
-    for bn in (128, 256):
+    for bn in (256, 512):
         x1 = torch.randn(B, H, W, C1, device=dev).half()
         x2 = torch.randn(B, H, W, C2, device=dev).half() if C2 else None
         w = (torch.randn(Cout, taps * (C1 + C2), device=dev) * 0.02).half()

@@ -8,6 +8,8 @@ import sys
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 agg = collections.defaultdict(lambda: [0, 0.0])
 for row in csv.DictReader(lines):
+    if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+        continue
     try:
         v = float(row["Metric Value"].replace(",", ""))
     except (ValueError, KeyError):
