@@ -21,16 +21,22 @@ namespace pdr {
 
 static constexpr double HPR_WSCALE = 1048576.0;        // 2^20: exact rescale of w
 static constexpr double HPR_BOX = 1073741824.0;        // |a|,|b| <= 2^30 (slope cap)
-static constexpr int HPR_TILE = 256;
+static constexpr int HPR_TILE = 128;
 
-// frames: [V][12] doubles = eye(3), ex(3), ey(3), ez(3)
+// frames: [V][12] doubles = eye(3), ex(3), ey(3), ez(3).
+// Output Q[v][k] = (u, v, w, 0) of point perm(k): the constraints are stored in the pseudo-random
+// visiting order, so every scan below is a sequential, fully coalesced 32-byte-per-lane stream.
+__device__ __forceinline__ int hpr_perm(int k, int N, int stride, int offset) {
+  return (int)(((long long)k * stride + offset) % N);
+}
+
 __global__ void hpr_prepare_kernel(const float* __restrict__ points, int N, int V,
-                                   const double* __restrict__ frames, double radius,
-                                   double* __restrict__ U, double* __restrict__ Vv,
-                                   double* __restrict__ Wt) {
+                                   const double* __restrict__ frames, double radius, int stride,
+                                   int offset, double4* __restrict__ Q) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)V * N) return;
-  const int v = i / N, n = i % N;
+  const int v = i / N, k = i % N;
+  const int n = hpr_perm(k, N, stride, offset);
   const double* f = frames + v * 12;
   const double px = (double)points[3 * n] - f[0], py = (double)points[3 * n + 1] - f[1],
                pz = (double)points[3 * n + 2] - f[2];
@@ -39,50 +45,53 @@ __global__ void hpr_prepare_kernel(const float* __restrict__ points, int N, int 
   const double x = px * f[3] + py * f[4] + pz * f[5];
   const double y = px * f[6] + py * f[7] + pz * f[8];
   const double z = px * f[9] + py * f[10] + pz * f[11];
-  U[i] = x / z;
-  Vv[i] = y / z;
-  Wt[i] = -HPR_WSCALE / (s * z);
+  Q[i] = make_double4(x / z, y / z, -HPR_WSCALE / (s * z), 0.0);
 }
 
-__device__ __forceinline__ int hpr_perm(int k, int N, int stride, int offset) {
-  return (int)(((long long)k * stride + offset) % N);
+// tighten [lo, hi] on the line p0 + t d with one earlier constraint; divisions only when the bound
+// actually moves (rare), comparisons by cross-multiplication otherwise
+__device__ __forceinline__ void hpr_clip(const double4 c, double uL, double vL, double wL,
+                                         double p0x, double p0y, double dx, double dy, double& lo,
+                                         double& hi) {
+  const double ax = c.x - uL, ay = c.y - vL, ah = c.z - wL;
+  const double den = ax * dx + ay * dy;
+  const double rhs = ah - (ax * p0x + ay * p0y);
+  if (den > 0.0) {
+    if (rhs > lo * den) lo = rhs / den;
+  } else if (den < 0.0) {
+    if (rhs > hi * den) hi = rhs / den;  // rhs/den < hi  <=>  rhs > hi*den  (den < 0)
+  } else if (rhs > 0.0) {
+    lo = INFINITY;
+  }
 }
 
-__global__ void __launch_bounds__(128)
-hpr_lp_kernel(const double* __restrict__ U, const double* __restrict__ Vv,
-              const double* __restrict__ Wt, int N, int stride, int offset,
+// one warp per block: warps re-solve at very different times, so nothing may couple them
+__global__ void __launch_bounds__(32)
+hpr_lp_kernel(const double4* __restrict__ Q, int N, int stride, int offset,
               uint8_t* __restrict__ vis) {
-  __shared__ double su[HPR_TILE], sv[HPR_TILE], sw[HPR_TILE];
-  __shared__ int sj[HPR_TILE];
+  __shared__ double4 sq[HPR_TILE];
   const int v = blockIdx.y;
-  const double* u = U + (size_t)v * N;
-  const double* vv = Vv + (size_t)v * N;
-  const double* w = Wt + (size_t)v * N;
+  const double4* q = Q + (size_t)v * N;
   const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active0 = i < N;
-  const double ui = active0 ? u[i] : 0.0, vi = active0 ? vv[i] : 0.0, wi = active0 ? w[i] : 0.0;
+  const int pi = blockIdx.x * 32 + lane;  // this lane's point, as a POSITION in visiting order
+  const bool active0 = pi < N;
+  const double4 me = active0 ? q[pi] : make_double4(0.0, 0.0, 0.0, 0.0);
+  const double ui = me.x, vi = me.y, wi = me.z;
   // maximise c.x with c = (1, 0.5) inside the box: start at the (+,+) corner
   double a = HPR_BOX, b = HPR_BOX;
   bool feasible = active0;
   const double c0 = 1.0, c1 = 0.5;
 
   for (int base = 0; base < N; base += HPR_TILE) {
-    __syncthreads();
-    for (int t = threadIdx.x; t < HPR_TILE && base + t < N; t += blockDim.x) {
-      const int j = hpr_perm(base + t, N, stride, offset);
-      sj[t] = j;
-      su[t] = u[j];
-      sv[t] = vv[j];
-      sw[t] = w[j];
-    }
-    __syncthreads();
-    if (!__any_sync(0xffffffffu, feasible)) continue;  // warp finished; keep hitting the barriers
+    if (!__any_sync(0xffffffffu, feasible)) break;  // every point of this warp is decided
+    __syncwarp();
+    for (int t = lane; t < HPR_TILE && base + t < N; t += 32) sq[t] = q[base + t];
+    __syncwarp();
     const int cnt = min(HPR_TILE, N - base);
     for (int t = 0; t < cnt; ++t) {
-      const int j = sj[t];
-      const double du = su[t] - ui, dv = sv[t] - vi, dw = sw[t] - wi;
-      const bool viol = feasible && j != i && (du * a + dv * b < dw);
+      const double4 cj = sq[t];
+      const double du = cj.x - ui, dv = cj.y - vi, dw = cj.z - wi;
+      const bool viol = feasible && (base + t) != pi && (du * a + dv * b < dw);
       unsigned m = __ballot_sync(0xffffffffu, viol);
       while (m) {
         const int L = __ffs(m) - 1;
@@ -90,8 +99,8 @@ hpr_lp_kernel(const double* __restrict__ U, const double* __restrict__ Vv,
         // everything about lane L's sub-problem, broadcast to the warp
         const double uL = __shfl_sync(0xffffffffu, ui, L), vL = __shfl_sync(0xffffffffu, vi, L),
                      wL = __shfl_sync(0xffffffffu, wi, L);
-        const int iL = __shfl_sync(0xffffffffu, i, L);
-        const double nx = su[t] - uL, ny = sv[t] - vL, h = sw[t] - wL;
+        const int pL = __shfl_sync(0xffffffffu, pi, L);
+        const double nx = cj.x - uL, ny = cj.y - vL, h = cj.z - wL;
         const double nn = nx * nx + ny * ny;
         double lo = -INFINITY, hi = INFINITY;
         double p0x = 0.0, p0y = 0.0, dx = 0.0, dy = 0.0;
@@ -115,21 +124,19 @@ hpr_lp_kernel(const double* __restrict__ U, const double* __restrict__ Vv,
           } else if (fabs(p0y) > HPR_BOX) {
             ok = false;
           }
-          // all earlier constraints (positions < base + t), split over the lanes
+          // all earlier constraints (positions < base + t), split over the lanes, 4 loads in flight
           const int pos = base + t;
-          for (int k = lane; k < pos; k += 32) {
-            const int jk = hpr_perm(k, N, stride, offset);
-            if (jk == iL) continue;
-            const double kx = u[jk] - uL, ky = vv[jk] - vL, kh = w[jk] - wL;
-            const double den = kx * dx + ky * dy;
-            const double rhs = kh - (kx * p0x + ky * p0y);
-            if (den > 0.0)
-              lo = fmax(lo, rhs / den);
-            else if (den < 0.0)
-              hi = fmin(hi, rhs / den);
-            else if (rhs > 0.0)
-              lo = INFINITY;
+          int k = lane;
+          for (; k + 96 < pos; k += 128) {
+            double4 c4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) c4[r] = q[k + 32 * r];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+              if (k + 32 * r != pL) hpr_clip(c4[r], uL, vL, wL, p0x, p0y, dx, dy, lo, hi);
           }
+          for (; k < pos; k += 32)
+            if (k != pL) hpr_clip(q[k], uL, vL, wL, p0x, p0y, dx, dy, lo, hi);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, o));
@@ -149,39 +156,37 @@ hpr_lp_kernel(const double* __restrict__ U, const double* __restrict__ Vv,
       }
     }
   }
-  if (active0) vis[(size_t)v * N + i] = feasible ? 1 : 0;
+  if (active0) vis[(size_t)v * N + hpr_perm(pi, N, stride, offset)] = feasible ? 1 : 0;
 }
 
-size_t hpr_workspace_bytes(int V, int N) { return (size_t)V * N * 3 * sizeof(double) + 256; }
+size_t hpr_workspace_bytes(int V, int N) { return (size_t)V * N * sizeof(double4) + 256; }
 
 int hpr_launch(const float* points, int N, int V, const double* frames_dev, double radius,
                void* workspace, uint8_t* vis, cudaStream_t stream) {
   PDR_CHECK_ARG(N > 0 && V > 0, "hidden point removal: empty input");
-  double* U = (double*)workspace;
-  double* Vv = U + (size_t)V * N;
-  double* Wt = Vv + (size_t)V * N;
-  hpr_prepare_kernel<<<cdiv((size_t)V * N, 256), 256, 0, stream>>>(points, N, V, frames_dev, radius,
-                                                                  U, Vv, Wt);
-  PDR_COUNT_LAUNCH();
+  PDR_CHECK_ARG(((uintptr_t)workspace & 31) == 0, "hidden point removal: workspace must be 32-byte aligned");
+  double4* Q = (double4*)workspace;
   // visiting order of the constraints: k -> (k*stride + offset) mod N, stride coprime with N
-  static const int primes[] = {7919, 104729, 1299709, 15485863, 32452843};
-  int stride = 1;
-  for (int p : primes)
-    if (N % p != 0 && p % N != 0) {
-      stride = p % N;
-      break;
-    }
-  // make sure gcd(stride, N) == 1
-  auto gcd = [](int x, int y) {
+  auto gcd = [](long long x, long long y) {
     while (y) {
-      int t = x % y;
+      long long t = x % y;
       x = y;
       y = t;
     }
     return x;
   };
-  while (stride < 1 || gcd(stride, N) != 1) stride = (stride + 1) % N == 0 ? 1 : stride + 1;
-  hpr_lp_kernel<<<dim3(cdiv(N, 128), V), 128, 0, stream>>>(U, Vv, Wt, N, stride, N / 3, vis);
+  int stride = 1;
+  for (int p : {7919, 104729, 1299709, 15485863, 32452843}) {
+    if (gcd(p % N, N) == 1 && p % N > 1) {
+      stride = p % N;
+      break;
+    }
+  }
+  const int offset = N / 3;
+  hpr_prepare_kernel<<<cdiv((size_t)V * N, 256), 256, 0, stream>>>(points, N, V, frames_dev, radius,
+                                                                  stride, offset, Q);
+  PDR_COUNT_LAUNCH();
+  hpr_lp_kernel<<<dim3(cdiv(N, 32), V), 32, 0, stream>>>(Q, N, stride, offset, vis);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;
