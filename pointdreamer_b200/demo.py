@@ -130,6 +130,57 @@ def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, c
     return vertices, uvs, faces, mesh_tex_idx, atlas_img, mask
 
 
+def colorize_batch(scenes, camera_info, cfg, inpainter, device):
+    """BASELINE.json configs[3]: several shapes at once on one GPU.  PROJECT and UNPROJECT run per
+    shape; all S*V diffusion chains run as ONE U-Net batch (chain s*V+v keeps the noise-stream slot
+    the reference's serial loop over shapes and views would give it).  `scenes`: list of dicts with
+    device tensors xyz, rgb, vertices, faces, f_normals, xatlas_dict.  Returns a list of atlases.
+    Only the path itself (complete_unseen_by in {None,'unproject'}, optimize_from None)."""
+    keys = {k: cfg[k] for k in PATH_CONFIG_KEYS}
+    V, res, cam_res = keys["view_num"], keys["res"], keys["cam_res"]
+    if keys["texture_gen_method"] != "DDNM_inpaint":
+        return [colorize_one_mesh(sc["xyz"], sc["rgb"], sc["vertices"], sc["faces"],
+                                  sc["f_normals"], sc["xatlas_dict"], camera_info, device=device,
+                                  save_img_path=None, inpainter=inpainter, glctx=None, logger=None,
+                                  **keys)[4] for sc in scenes]
+    cams = camera_info['cams']
+    staged = []
+    with torch.no_grad():
+        for sc in scenes:
+            (hard_masks, _, depths, _, uv_centers, uv_scales, padding, point_uvs,
+             point_depths) = _ou.get_rendered_hard_mask_and_face_idx_batch(
+                cams, sc["vertices"], sc["faces"], sc["xyz"], glctx=None, rescale=keys["crop_img"],
+                padding=keys["crop_padding"])
+            if cam_res != res:
+                hard_masks = _ou.resize_hard_masks(hard_masks, res)
+            pv, _ = _ou.get_point_validation_by_depth(cam_res, point_uvs, point_depths, depths,
+                                                      offset=0.0001)
+            if keys["point_validation_by_o3d"]:
+                pv = torch.logical_or(pv, _ou.get_point_validation_by_o3d(
+                    sc["xyz"], camera_info['eye_positions'], keys["hidden_point_removal_radius"]))
+            pp = _ou.get_point_pixels(point_uvs, res)
+            sparse, m0, m2, scales = _ou.get_sparse_images(
+                pp, sc["rgb"], pv, hard_masks, None, V, res, keys["point_size"],
+                keys["edge_point_size"], keys["mask_ratio_thresh"])
+            staged.append(dict(sparse=sparse, m2=m2, scales=scales, depths=depths,
+                               uv_centers=uv_centers, uv_scales=uv_scales, padding=padding))
+        inpainted = inpainter.inpaint_batch(torch.cat([s_["sparse"] for s_ in staged], 0),
+                                            torch.cat([s_["m2"][:, 0] for s_ in staged], 0))
+        atlases = []
+        for i, (sc, st) in enumerate(zip(scenes, staged)):
+            xa = sc["xatlas_dict"]
+            atlas = _un.unproject(inpainted[i * V:(i + 1) * V], sc["vertices"], sc["f_normals"], res,
+                                  cams, cam_res, camera_info['base_dirs'], xa["gb_pos"], xa["mask"],
+                                  xa["per_atlas_pixel_face_id"], st["uv_centers"], st["uv_scales"],
+                                  st["padding"], st["scales"], st["depths"],
+                                  keys["edge_dilate_kernels"], None,
+                                  keys["complete_unseen_by"] == 'unproject')[0]
+            if keys["complete_unseen_by"] == 'unproject':
+                atlas = _un.dilate_atlas(atlas, xa["mask"])
+            atlases.append(atlas)
+    return atlases
+
+
 def colorize_from_host(scene, camera_info, cfg, inpainter, device):
     """End-to-end convenience used by bench.py's `e2e` leg: every input starts in (pinned) HOST
     memory, is copied to the device, run through colorize_one_mesh, and the atlas is copied back.

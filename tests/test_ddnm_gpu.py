@@ -121,3 +121,30 @@ def test_chain_small_vs_oracle(cuda):
         m3 = torch.from_numpy(masks[v]).to(cuda)[None, :, :, None].repeat(1, 1, 1, 3)
         o = inp2.inpaint(torch.from_numpy(sparse[v]).to(cuda).permute(1, 2, 0)[None], m3)
         assert np.array_equal(o[0].cpu().numpy(), out[v])
+
+
+def test_colorize_batch_equals_serial(cuda):
+    """configs[3] path: shapes batched through one U-Net batch == shape-by-shape calls (bit-exact,
+    chains keep their slot of the noise stream)."""
+    from pointdreamer_b200 import demo, synthetic
+    from pointdreamer_b200.ddnm_inpainting import DEFAULT_DDNM_CONFIG, Inpainter
+    sd = ounet.synthetic_state_dict(SMALL, seed=5)
+    cfg = dict(demo.DEFAULT_CONFIG, view_num=2, res=64, cam_res=128, xatlas_texture_res=256,
+               edge_dilate_kernels=[5], optimize_from=None, complete_unseen_by="unproject")
+    dd = dict(DEFAULT_DDNM_CONFIG, T_sampling=3)
+    cam = demo.prepare_cameras(cfg, cuda)
+    scenes = []
+    for seed in (1, 2, 3):
+        sc = synthetic.make_scene(2000, seed=seed, nu=16, nv=16, atlas_res=256, charts=(2, 2))
+        d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(cuda) for k, v in sc.items() if k != "xatlas_dict"}
+        d["xatlas_dict"] = {k: torch.from_numpy(v).to(cuda) for k, v in sc["xatlas_dict"].items()}
+        scenes.append(d)
+    inp = Inpainter(cuda, state_dict=sd, model_config=SMALL, ddnm_config=dd, seed=42, offset=0)
+    batched = demo.colorize_batch(scenes, cam, cfg, inp, cuda)
+    inp2 = Inpainter(cuda, state_dict=sd, model_config=SMALL, ddnm_config=dd, seed=42, offset=0)
+    keys = {k: cfg[k] for k in demo.PATH_CONFIG_KEYS}
+    for sc, a in zip(scenes, batched):
+        out = demo.colorize_one_mesh(sc["xyz"], sc["rgb"], sc["vertices"], sc["faces"], sc["f_normals"],
+                                     sc["xatlas_dict"], cam, device=cuda, save_img_path=None,
+                                     inpainter=inp2, glctx=None, logger=None, **keys)
+        assert torch.equal(out[4], a)
