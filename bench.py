@@ -303,10 +303,15 @@ def main():
     conv = prof["conv_tc"]
     conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
     total_prof_ms = sum(v["ms"] for v in prof.values())
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01f_conv_traffic.json")
+    if os.path.exists(tp):  # DRAM bytes per conv launch from the committed ncu capture
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["avg_traffic_bytes_per_launch"], tj["source"]
     roofline = {
         "bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": conv_tflops / peak_tf, "traffic": None,
-        "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv)",
+        "frac": conv_tflops / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+        "kernel": "conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv, 2-CTA and 1-CTA)",
         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
         "launch_avg_ms": conv["ms"] / max(conv["launches"], 1),
         "flops_per_launch_avg": conv["flops"] / max(conv["launches"], 1),

@@ -23,6 +23,8 @@ l0 = _lib.launch_count()
 y = eng(x, t)
 torch.cuda.synchronize()
 print("launches per forward", _lib.launch_count() - l0, "out std", y.std().item(), "finite", torch.isfinite(y).all().item())
+if os.environ.get("PDR_QUICK"):
+    sys.exit(0)
 for _ in range(2):
     eng(x, t)
 torch.cuda.synchronize()
