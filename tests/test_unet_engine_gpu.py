@@ -89,3 +89,21 @@ def test_engine_rejects_missing_param(cuda):
     eng = UNetEngine(sd, SMALL, device=cuda)
     with pytest.raises(_lib.PdrError):
         eng.plan(1)
+
+
+def test_engine_full_size_vs_oracle(cuda):
+    """The production model (imagenet_256.yml: 552.8M parameters, 256^2) at batch 2 — large enough
+    for the 2-CTA conv path — against the fp16-emulating oracle on the host."""
+    from pointdreamer_b200.unet import DEFAULT_MODEL_CONFIG, UNetEngine, random_state_dict
+    sd = random_state_dict(DEFAULT_MODEL_CONFIG, seed=21, device="cpu")
+    eng = UNetEngine(sd, DEFAULT_MODEL_CONFIG, device=cuda)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 256, 256, generator=gen)
+    t = torch.tensor([870.0, 120.0])
+    y = eng(x.to(cuda), t.to(cuda)).cpu().numpy()
+    o16 = ounet.UNetOracle(sd, ounet.DEFAULT_CONFIG, emulate_fp16=True).forward(x, t).numpy()
+    rel = np.linalg.norm(y - o16) / np.linalg.norm(o16)
+    print(f"full model: engine vs oracle16 max abs {np.abs(y - o16).max():.3e}, rel L2 {rel:.3e}, "
+          f"out std {o16.std():.3f}")
+    assert np.isfinite(y).all()
+    assert rel < 3e-3 and np.abs(y - o16).max() < 2e-2
