@@ -62,7 +62,7 @@ int pdr_resample(const void* x, int B, int H, int W, int C, int mode, void* out,
 }
 int pdr_attention(const void* qkv, int B, int T, int heads, void* out, void* stream) {
   PDR_CHECK_ARG(qkv && out, "pdr_attention: null pointer");
-  return attention_launch((const __half*)qkv, B, T, heads, (__half*)out, (cudaStream_t)stream);
+  return attention_launch((const __half*)qkv, B, T, heads, 0, (__half*)out, (cudaStream_t)stream);
 }
 int pdr_unet_head(const void* h, const float* gamma, const float* beta, const float* w,
                   const float* bias, int B, int H, int W, int C, int n_out, float* ws,

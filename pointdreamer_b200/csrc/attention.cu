@@ -5,109 +5,149 @@
 // c = head*(3*64) + {q:0..63, k:64..127, v:128..191}.  Rounding points mirror the reference's
 // fp16 tensors: q*scale and k*scale (scale = 64^-1/4) are fp16, the logits are an fp16 tensor,
 // softmax runs in fp32 and is cast to fp16, the weighted sum is an fp16 tensor.
-// Attention is 0.5 % of the U-Net's FLOPs: this kernel favours exactness over
-// speed — two passes over the keys (row max / sum, then normalised probabilities x V) with
-// mma.sync m16n8k16 tiles; no T x T matrix is ever written to HBM.
+// Because the normalised probabilities are rounded to fp16 BEFORE the weighted sum, the row max
+// and row sum must be final before any P is formed: two passes over the keys (row max / sum of
+// exp, then P = fp16(exp(s-m)/l) and O += P V), mma.sync m16n8k16 with ldmatrix fragments; K/V
+// tiles are double buffered in shared memory with the next tile's global loads in flight during
+// the current tile's math; no T x T matrix is ever written to HBM.  q and k arrive either raw
+// (scaled here while staging) or already scaled by the qkv conv's epilogue (PRESCALED).
 #include "common.cuh"
 #include "unet_ops.h"
 
 namespace pdr {
 
 static constexpr int DH = 64;       // head dim
-static constexpr int QT = 64;       // queries per CTA
 static constexpr int KT = 64;       // keys per tile
-static constexpr int LDS = 72;      // padded smem row (halfs)
+static constexpr int LDS = 72;      // padded smem row (halfs): 144 B, conflict-free for ldmatrix
+static constexpr float LOG2E = 1.4426950408889634f;
+static constexpr float QK_SCALE = 0.35355339059327373f;  // 1/sqrt(sqrt(64))
 
-__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
-                                          const uint32_t (&b)[2]) {
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                          uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
       "{%0,%1,%2,%3};\n"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const __half* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __half* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(a));
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *(uint32_t*)&h;
 }
-
-// load a [64 x 64] tile (rows = tokens) of q, k or v into smem, optionally scaled (fp16 result)
-__device__ __forceinline__ void load_tile(const __half* __restrict__ src, int row_stride,
-                                          float scale, bool do_scale, __half* dst /*[64][LDS]*/) {
-  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
-    const int r = i >> 3, c8 = (i & 7) * 8;
-    uint4 v = __ldg((const uint4*)(src + (size_t)r * row_stride + c8));
-    if (do_scale) {
-      __half* h = (__half*)&v;
+// fp16(float(h) * scale) on 8 packed halfs (the reference's `q * scale` on an fp16 tensor)
+__device__ __forceinline__ uint4 scale8(uint4 v, float scale) {
+  __half2* h = (__half2*)&v;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(__half2float(h[j]) * scale);
-    }
-    *(uint4*)(dst + r * LDS + c8) = v;
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(h[j]);
+    h[j] = __floats2half2_rn(f.x * scale, f.y * scale);
   }
-}
-__device__ __forceinline__ void load_tile_transposed(const __half* __restrict__ src,
-                                                     int row_stride, __half* dst /*[64 d][LDS]*/) {
-  for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
-    const int r = i >> 3, c8 = (i & 7) * 8;  // r = key, c8 = first of 8 d's
-    const uint4 v = __ldg((const uint4*)(src + (size_t)r * row_stride + c8));
-    const __half* h = (const __half*)&v;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dst[(c8 + j) * LDS + r] = h[j];
-  }
+  return v;
 }
 
-// S = Q K^T for this warp's 16 query rows against the 64 keys in sK; result rounded to fp16
-__device__ __forceinline__ void compute_scores(const __half* sQ, const __half* sK, int warp,
+// S = Q K^T for this warp's 16 query rows against the 64 keys in sK, rounded to fp16 values
+// (the logits are an fp16 tensor in the reference)
+__device__ __forceinline__ void compute_scores(const uint32_t (&qf)[4][4], const __half* sK,
                                                int lane, float (&s)[8][4]) {
-  const int r0 = warp * 16 + (lane >> 2);
-  const int cq = (lane & 3) * 2;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int j = 0; j < 4; ++j) s[nt][j] = 0.f;
+  const __half* kp = sK + (lane & 7) * LDS + (lane >> 3) * 8;
 #pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    uint32_t a[4];
-    a[0] = *(const uint32_t*)(sQ + r0 * LDS + ks * 16 + cq);
-    a[1] = *(const uint32_t*)(sQ + (r0 + 8) * LDS + ks * 16 + cq);
-    a[2] = *(const uint32_t*)(sQ + r0 * LDS + ks * 16 + 8 + cq);
-    a[3] = *(const uint32_t*)(sQ + (r0 + 8) * LDS + ks * 16 + 8 + cq);
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      uint32_t b[2];
-      const int kr = nt * 8 + (lane >> 2);
-      b[0] = *(const uint32_t*)(sK + kr * LDS + ks * 16 + cq);
-      b[1] = *(const uint32_t*)(sK + kr * LDS + ks * 16 + 8 + cq);
-      mma_16816(s[nt], a, b);
-    }
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t b01[4], b23[4];
+    ldsm_x4(b01, kp + nt * 8 * LDS);        // d 0..31  -> k-steps 0, 1
+    ldsm_x4(b23, kp + nt * 8 * LDS + 32);   // d 32..63 -> k-steps 2, 3
+    mma_16816(s[nt], qf[0], b01[0], b01[1]);
+    mma_16816(s[nt], qf[1], b01[2], b01[3]);
+    mma_16816(s[nt], qf[2], b23[0], b23[1]);
+    mma_16816(s[nt], qf[3], b23[2], b23[3]);
   }
 #pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s[nt][j] = round_h(s[nt][j]);  // logits are an fp16 tensor
+  for (int nt = 0; nt < 8; ++nt) {
+    const float2 lo = __half22float2(__floats2half2_rn(s[nt][0], s[nt][1]));
+    const float2 hi = __half22float2(__floats2half2_rn(s[nt][2], s[nt][3]));
+    s[nt][0] = lo.x, s[nt][1] = lo.y, s[nt][2] = hi.x, s[nt][3] = hi.y;
+  }
 }
 
-__global__ void __launch_bounds__(128)
+// NW warps, 16 query rows each.  Tiles of 64 keys; per tile every thread moves TPT 16-byte chunks
+// of K (and of V in pass 2) from global to shared memory through registers.
+template <int NW, bool PRESCALED>
+__global__ void __launch_bounds__(NW * 32, 16 / NW)
 attention_kernel(const __half* __restrict__ qkv, int T, int heads, __half* __restrict__ out) {
-  __shared__ __align__(16) __half sQ[QT * LDS];
-  __shared__ __align__(16) __half sK[KT * LDS];
-  __shared__ __align__(16) __half sVt[DH * LDS];
+  constexpr int NT = NW * 32;
+  constexpr int QT = NW * 16;
+  constexpr int TPT = 64 * 8 / NT;  // 16-byte chunks of one 64x64 tile per thread (4 or 2)
+  __shared__ __align__(16) __half sK[2][KT * LDS];
+  __shared__ __align__(16) __half sV[2][KT * LDS];  // pass-2 V tiles; first the Q staging area
+  static_assert(QT * LDS <= 2 * KT * LDS, "Q staging must fit in the V buffers");
   const int qt = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
   const int C3 = heads * 3 * DH, C = heads * DH;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float scale = 0.35355339059327373f;  // 1/sqrt(sqrt(64))
   const __half* base = qkv + (size_t)b * T * C3 + head * 3 * DH;
-  load_tile(base + (size_t)qt * QT * C3, C3, scale, true, sQ);
+  const int nkt = T / KT;
+
+  // ---- Q tile -> smem -> A fragments held in registers for the whole kernel ----
+  {
+    __half* sQ = &sV[0][0];
+    const __half* qsrc = base + (size_t)qt * QT * C3;
+    for (int i = threadIdx.x; i < QT * 8; i += NT) {
+      const int r = i >> 3, c8 = (i & 7) * 8;
+      uint4 v = __ldg((const uint4*)(qsrc + (size_t)r * C3 + c8));
+      if (!PRESCALED) v = scale8(v, QK_SCALE);
+      *(uint4*)(sQ + r * LDS + c8) = v;
+    }
+  }
+  uint4 kreg[TPT], vreg[TPT];
+  auto gload = [&](int kt, int which /*1 = k, 2 = v*/, uint4 (&reg)[TPT]) {
+    const __half* src = base + (size_t)kt * KT * C3 + which * DH;
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) {
+      const int i = threadIdx.x + j * NT;
+      reg[j] = __ldg((const uint4*)(src + (size_t)(i >> 3) * C3 + (i & 7) * 8));
+    }
+  };
+  auto sstore = [&](__half* dst, const uint4 (&reg)[TPT], bool scale) {
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) {
+      const int i = threadIdx.x + j * NT;
+      *(uint4*)(dst + (i >> 3) * LDS + (i & 7) * 8) = scale ? scale8(reg[j], QK_SCALE) : reg[j];
+    }
+  };
+  gload(0, 1, kreg);
+  __syncthreads();
+  uint32_t qf[4][4];
+  {
+    const __half* qp = &sV[0][0] + (warp * 16 + (lane & 15)) * LDS + (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldsm_x4(qf[ks], qp + ks * 16);
+  }
+  sstore(sK[0], kreg, !PRESCALED);
+  __syncthreads();  // Q fragments read by every warp before the V buffers are reused
 
   float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
   float s[8][4];
   // ---- pass 1: row max and sum of exp ----
-  for (int kt = 0; kt < T / KT; ++kt) {
-    __syncthreads();
-    load_tile(base + (size_t)kt * KT * C3 + DH, C3, scale, true, sK);
-    __syncthreads();
-    compute_scores(sQ, sK, warp, lane, s);
+  for (int kt = 0; kt < nkt; ++kt) {
+    // the tile after the last K tile of pass 1 is K tile 0 of pass 2 (+ V tile 0)
+    const int nk = kt + 1 < nkt ? kt + 1 : 0;
+    gload(nk, 1, kreg);
+    if (kt + 1 == nkt) gload(0, 2, vreg);
+    compute_scores(qf, sK[kt & 1], lane, s);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float tm = -INFINITY;
@@ -118,44 +158,57 @@ attention_kernel(const __half* __restrict__ qkv, int T, int heads, __half* __res
       const float mn = fmaxf(m[h], tm);
       float ts = 0.f;
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) ts += expf(s[nt][2 * h] - mn) + expf(s[nt][2 * h + 1] - mn);
+      for (int nt = 0; nt < 8; ++nt)
+        ts += exp2f((s[nt][2 * h] - mn) * LOG2E) + exp2f((s[nt][2 * h + 1] - mn) * LOG2E);
       ts += __shfl_xor_sync(0xffffffffu, ts, 1);
       ts += __shfl_xor_sync(0xffffffffu, ts, 2);
-      l[h] = l[h] * expf(m[h] - mn) + ts;
+      l[h] = l[h] * exp2f((m[h] - mn) * LOG2E) + ts;
       m[h] = mn;
     }
+    sstore(sK[(kt + 1) & 1], kreg, !PRESCALED);
+    if (kt + 1 == nkt) sstore(sV[0], vreg, false);
+    __syncthreads();
   }
-  // ---- pass 2: P = softmax (fp16), O = P V ----
+  const float inv_l[2] = {1.f / l[0], 1.f / l[1]};
+  // ---- pass 2: P = fp16(softmax), O += P V ----
   float o[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[nt][j] = 0.f;
-  for (int kt = 0; kt < T / KT; ++kt) {
-    __syncthreads();
-    load_tile(base + (size_t)kt * KT * C3 + DH, C3, scale, true, sK);
-    load_tile_transposed(base + (size_t)kt * KT * C3 + 2 * DH, C3, sVt);
-    __syncthreads();
-    compute_scores(sQ, sK, warp, lane, s);
+  const int kb0 = nkt & 1;  // K buffer that holds pass-2 tile 0
+  for (int kt = 0; kt < nkt; ++kt) {
+    if (kt + 1 < nkt) {
+      gload(kt + 1, 1, kreg);
+      gload(kt + 1, 2, vreg);
+    }
+    compute_scores(qf, sK[(kb0 + kt) & 1], lane, s);
     uint32_t p[8][2];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      p[nt][0] = pack_h2(expf(s[nt][0] - m[0]) / l[0], expf(s[nt][1] - m[0]) / l[0]);
-      p[nt][1] = pack_h2(expf(s[nt][2] - m[1]) / l[1], expf(s[nt][3] - m[1]) / l[1]);
+      p[nt][0] = pack_h2(exp2f((s[nt][0] - m[0]) * LOG2E) * inv_l[0],
+                         exp2f((s[nt][1] - m[0]) * LOG2E) * inv_l[0]);
+      p[nt][1] = pack_h2(exp2f((s[nt][2] - m[1]) * LOG2E) * inv_l[1],
+                         exp2f((s[nt][3] - m[1]) * LOG2E) * inv_l[1]);
     }
-    const int cq = (lane & 3) * 2;
+    // V^T fragments straight from the [key][d] tile with ldmatrix.trans
+    const __half* vp = sV[kt & 1] + ((lane & 7) + ((lane >> 3) & 1) * 8) * LDS + (lane >> 4) * 8;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-      uint32_t a[4] = {p[2 * ks][0], p[2 * ks][1], p[2 * ks + 1][0], p[2 * ks + 1][1]};
+      const uint32_t a[4] = {p[2 * ks][0], p[2 * ks][1], p[2 * ks + 1][0], p[2 * ks + 1][1]};
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        uint32_t bb[2];
-        const int dr = nt * 8 + (lane >> 2);
-        bb[0] = *(const uint32_t*)(sVt + dr * LDS + ks * 16 + cq);
-        bb[1] = *(const uint32_t*)(sVt + dr * LDS + ks * 16 + 8 + cq);
-        mma_16816(o[nt], a, bb);
+      for (int np = 0; np < 4; ++np) {
+        uint32_t bv[4];
+        ldsm_x4_t(bv, vp + ks * 16 * LDS + np * 16);  // d-blocks 2np, 2np+1 of keys ks*16..+15
+        mma_16816(o[2 * np], a, bv[0], bv[1]);
+        mma_16816(o[2 * np + 1], a, bv[2], bv[3]);
       }
     }
+    if (kt + 1 < nkt) {
+      sstore(sK[(kb0 + kt + 1) & 1], kreg, !PRESCALED);
+      sstore(sV[(kt + 1) & 1], vreg, false);
+    }
+    __syncthreads();
   }
   // ---- write O (fp16) ----
   const int r0 = qt * QT + warp * 16 + (lane >> 2);
@@ -168,14 +221,27 @@ attention_kernel(const __half* __restrict__ qkv, int T, int heads, __half* __res
   }
 }
 
-int attention_launch(const __half* qkv, int B, int T, int heads, __half* out,
-                     cudaStream_t stream) {
-  PDR_CHECK_ARG(T % 64 == 0 && T >= 64, "attention: sequence length %d must be a multiple of 64", T);
-  PDR_CHECK_ARG(heads >= 1 && B >= 1, "attention: bad shape");
-  attention_kernel<<<dim3(T / QT, heads, B), 128, 0, stream>>>(qkv, T, heads, out);
+template <int NW>
+static int attention_launch_nw(const __half* qkv, int B, int T, int heads, int prescaled,
+                               __half* out, cudaStream_t stream) {
+  const dim3 grid(T / (NW * 16), heads, B);
+  if (prescaled)
+    attention_kernel<NW, true><<<grid, NW * 32, 0, stream>>>(qkv, T, heads, out);
+  else
+    attention_kernel<NW, false><<<grid, NW * 32, 0, stream>>>(qkv, T, heads, out);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;
+}
+
+int attention_launch(const __half* qkv, int B, int T, int heads, int prescaled, __half* out,
+                     cudaStream_t stream) {
+  PDR_CHECK_ARG(T % 64 == 0 && T >= 64, "attention: sequence length %d must be a multiple of 64", T);
+  PDR_CHECK_ARG(heads >= 1 && B >= 1, "attention: bad shape");
+  // 128 queries per CTA halves the K/V re-reads; small maps keep 64 so the grid still fills
+  if (T % 128 == 0 && (T / 128) * heads * B >= 2 * 148)
+    return attention_launch_nw<8>(qkv, B, T, heads, prescaled, out, stream);
+  return attention_launch_nw<4>(qkv, B, T, heads, prescaled, out, stream);
 }
 
 }  // namespace pdr

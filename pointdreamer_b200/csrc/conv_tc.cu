@@ -42,6 +42,7 @@ struct ConvArgs {
   // optional fused GroupNorm statistics: per (m-tile, epilogue warp, 8-channel chunk) sum and
   // sum of squares of the fp16 outputs, [tiles_m][4][Cout/8][2] floats (null = off)
   float* stats_partial;
+  float qk_scale;  // != 0: channels with c % 192 < 128 are re-rounded after a multiply by it
 };
 
 template <int BN, int STAGES>
@@ -90,6 +91,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint32_t tme
         o[j + 1] = __float2half_rn(__uint_as_float(v[j + 1]) + bv.y);
         o[j + 2] = __float2half_rn(__uint_as_float(v[j + 2]) + bv.z);
         o[j + 3] = __float2half_rn(__uint_as_float(v[j + 3]) + bv.w);
+      }
+      if (args.qk_scale != 0.f && (nb % 192) < 128) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = __float2half_rn(__half2float(o[j]) * args.qk_scale);
       }
       if (args.residual) {
         // reference adds two fp16 tensors (unet.py:256, :305): fp32 add, one more rounding
@@ -639,7 +644,7 @@ static int launch_impl2(const ConvTensorMap* a1, const ConvTensorMap* a2, const 
 int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
                    int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, float qk_scale) {
   PDR_CHECK_ARG(taps == 9 || taps == 1, "taps must be 9 or 1 (got %d)", taps);
   PDR_CHECK_ARG(C1 > 0 && C1 % BLOCK_K == 0 && C2 % BLOCK_K == 0, "C1/C2 must be multiples of 64");
   PDR_CHECK_ARG(BN == 64 || BN == 128 || BN == 256 || BN == 512, "BN must be 64, 128, 256 or 512");
@@ -666,6 +671,9 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   args.residual = residual;
   args.out = out;
   args.stats_partial = stats_partial;
+  args.qk_scale = qk_scale;
+  PDR_CHECK_ARG(qk_scale == 0.f || (Cout % 192 == 0 && !residual && !stats_partial),
+                "qk_scale is for qkv projections (Cout %% 192 == 0, no residual, no statistics)");
   PDR_CHECK_ARG(!stats_partial || (args.bb == 1 && Cout % 32 == 0),
                 "fused GroupNorm statistics need one image per tile (H*W >= 128)");
   if (two_cta) {

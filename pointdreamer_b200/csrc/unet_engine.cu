@@ -260,7 +260,7 @@ class UnetEngine {
 
   // want_sums: also produce the GroupNorm sums of `out` in the epilogue (when the tile allows)
   int add_conv(const Act& x1, const Act* x2, const std::string& pname, int taps, const Act* res,
-               Act& out, bool want_sums = false) {
+               Act& out, bool want_sums = false, float qk_scale = 0.f) {
     const int stat_rows = want_sums && out.C % 256 == 0 ? conv_tc_stats_rows_per_image(out.H, out.W) : 0;
     if (stat_rows > 0) {
       out.has_sums = true;
@@ -294,7 +294,7 @@ class UnetEngine {
     ops.cur_flops = 2.0 * Bn * H * W * (double)Co * taps * (C1 + C2);
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return conv_tc_launch(&c->a1, has2 ? &c->a2 : nullptr, &c->w, bn, Bn, H, W, C1, C2, Co, taps,
-                            bias, r, o, partial, s);
+                            bias, r, o, partial, s, qk_scale);
     });
     if (stat_rows > 0) {
       double* sums = P<double>(out.sums_off);
@@ -378,7 +378,8 @@ class UnetEngine {
     Act n = new_act(x.H, x.W, C);
     PDR_TRY(add_gn_apply(x, nullptr, p + ".norm", 0, false, 0, false, 0, n));
     Act qkv = new_act(x.H, x.W, 3 * C);
-    PDR_TRY(add_conv(n, nullptr, p + ".qkv", 1, nullptr, qkv));
+    // q*scale and k*scale (unet.py:349-351) are applied by the projection's epilogue
+    PDR_TRY(add_conv(n, nullptr, p + ".qkv", 1, nullptr, qkv, false, 0.35355339059327373f));
     drop(n);
     Act a = new_act(x.H, x.W, C);
     if (!dry_) {
@@ -388,7 +389,7 @@ class UnetEngine {
       ops.cur_cls = PDR_OP_ATTENTION;
       ops.cur_flops = 4.0 * Bn * heads * (double)T * T * 64;
       ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
-        return attention_launch(q, Bn, T, heads, o, s);
+        return attention_launch(q, Bn, T, heads, 1, o, s);
       });
     }
     drop(qkv);

@@ -49,30 +49,49 @@ __global__ void linear_kernel(const float* __restrict__ in, const float* __restr
       s_in[i] = v;
     }
     __syncthreads();
-    for (int n = blockIdx.x * warps + warp; n < N; n += gridDim.x * warps) {
-      float acc[8];
+    // a warp owns LF consecutive output features at a time: LF independent 16-byte weight
+    // loads in flight per step and each staged input vector is read once for LF features
+    constexpr int LF = 4;
+    for (int n0 = (blockIdx.x * warps + warp) * LF; n0 < N; n0 += gridDim.x * warps * LF) {
+      float acc[LF][8];
 #pragma unroll
-      for (int b = 0; b < 8; ++b) acc[b] = 0.f;
-      const float* wr = W + (size_t)n * K;
+      for (int f = 0; f < LF; ++f)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[f][b] = 0.f;
+      const float* wr[LF];
+#pragma unroll
+      for (int f = 0; f < LF; ++f) wr[f] = W + (size_t)min(n0 + f, N - 1) * K;
       for (int k = lane * 4; k < K; k += 128) {
-        const float4 w4 = __ldg((const float4*)(wr + k));
+        float4 w4[LF];
+#pragma unroll
+        for (int f = 0; f < LF; ++f) w4[f] = __ldg((const float4*)(wr[f] + k));
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
           if (b < nb) {
-            const float* s = s_in + b * K + k;
-            acc[b] += w4.x * s[0] + w4.y * s[1] + w4.z * s[2] + w4.w * s[3];
+            const float4 s = *(const float4*)(s_in + b * K + k);
+#pragma unroll
+            for (int f = 0; f < LF; ++f)
+              acc[f][b] += w4[f].x * s.x + w4[f].y * s.y + w4[f].z * s.z + w4[f].w * s.w;
           }
         }
       }
 #pragma unroll
-      for (int b = 0; b < 8; ++b)
-        for (int o = 16; o > 0; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+      for (int f = 0; f < LF; ++f)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          for (int o = 16; o > 0; o >>= 1)
+            acc[f][b] += __shfl_xor_sync(0xffffffffu, acc[f][b], o);
       if (lane == 0) {
-        const float bv = bias ? bias[n] : 0.f;
-        for (int b = 0; b < nb; ++b) {
-          const float r = acc[b] + bv;
-          if (out) out[(size_t)(b0 + b) * N + n] = r;
-          if (out16) out16[(size_t)(b0 + b) * N + n] = __float2half_rn(r);
+#pragma unroll
+        for (int f = 0; f < LF; ++f) {
+          const int n = n0 + f;
+          if (n >= N) break;
+          const float bv = bias ? bias[n] : 0.f;
+          for (int b = 0; b < nb; ++b) {
+            const float r = acc[f][b] + bv;
+            if (out) out[(size_t)(b0 + b) * N + n] = r;
+            if (out16) out16[(size_t)(b0 + b) * N + n] = __float2half_rn(r);
+          }
         }
       }
     }
@@ -91,7 +110,7 @@ int linear_launch(const float* in, const float* W, const float* bias, int B, int
                                   8 * 4096 * 4));
     configured = true;
   }
-  int grid = cdiv(N, threads / 32);
+  int grid = cdiv(N, (threads / 32) * 4);
   if (grid > 148 * 8) grid = 148 * 8;
   linear_kernel<<<grid, threads, smem, stream>>>(in, W, bias, B, K, N, mode_in, out, out16);
   PDR_COUNT_LAUNCH();
@@ -313,11 +332,72 @@ int gn_stats_slabs(int B, int HW) {
   return slabs;
 }
 
+// Small feature maps (HW <= 256, 8-channel aligned groups): one block per (group, image) reads its
+// HW x C/32 slab once and writes (mean, rstd) directly - one launch, 32*B blocks, instead of the
+// two-stage slab reduction whose grid would be B blocks.  Fixed summation order.
+__global__ void __launch_bounds__(256)
+gn_stats_small_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, int C1, int C2,
+                      int HW, float eps, float* __restrict__ stats) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int C = C1 + C2, cpg = C / 32, chunks = cpg / 8;
+  const int planes = 256 / chunks;
+  const int chunk = threadIdx.x % chunks, plane = threadIdx.x / chunks;
+  const int c0 = g * cpg + chunk * 8;
+  const __half* src = c0 < C1 ? x1 + c0 : x2 + (c0 - C1);
+  const size_t stride = c0 < C1 ? C1 : C2;
+  src += (size_t)b * HW * stride;
+  float s = 0.f, q = 0.f;
+  if (plane < planes) {
+    for (int p = plane; p < HW; p += planes) {
+      const uint4 v = __ldg((const uint4*)(src + (size_t)p * stride));
+      const __half* h = (const __half*)&v;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f = h2f(h[j]);
+        s += f;
+        q += f * f;
+      }
+    }
+  }
+  double ds = (double)s, dq = (double)q;
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+  __shared__ double sm[8][2];
+  if ((threadIdx.x & 31) == 0) {
+    sm[threadIdx.x >> 5][0] = ds;
+    sm[threadIdx.x >> 5][1] = dq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      ts += sm[w][0];
+      tq += sm[w][1];
+    }
+    const double cnt = (double)HW * cpg;
+    const double mean = ts / cnt;
+    double var = tq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((size_t)b * 32 + g) * 2 + 0] = (float)mean;
+    stats[((size_t)b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 int gn_stats_launch(const __half* x1, const __half* x2, int B, int HW, int C1, int C2,
                     float* ws_partial, float* stats, cudaStream_t stream) {
   const int C = C1 + C2;
   PDR_CHECK_ARG(C % 32 == 0 && C1 % 8 == 0 && C2 % 8 == 0 && C <= 4096,
                 "GroupNorm32: unsupported channel count %d+%d", C1, C2);
+  if (HW <= 256 && C % 256 == 0 && C / 256 <= 256) {
+    gn_stats_small_kernel<<<dim3(32, B), 256, 0, stream>>>(x1, x2 ? x2 : x1, C1, C2, HW, 1e-5f,
+                                                           stats);
+    PDR_COUNT_LAUNCH();
+    PDR_LAUNCH_CHECK();
+    return 0;
+  }
   const int chunks = C / 8;
   const int threads = chunks >= 256 ? chunks : 256 / chunks * chunks;
   PDR_CHECK_ARG(threads <= 1024, "GroupNorm32: too many channels");
@@ -336,10 +416,11 @@ int gn_stats_launch(const __half* x1, const __half* x2, int B, int HW, int C1, i
 // ---- GroupNorm statistics fused into the producing conv (conv_tc epilogue) ----
 // reduce the epilogue's partial rows [B*R][C8][2] (fp32) to per-image per-8-channel sums
 // sums8[B][C8][2] (fp64), fixed summation order.
-__global__ void sums8_reduce_kernel(const float* __restrict__ partial, int R, int C8,
-                                    double* __restrict__ sums8) {
+template <int PARTS>
+__global__ void __launch_bounds__(32 * PARTS)
+sums8_reduce_kernel(const float* __restrict__ partial, int R, int C8,
+                    double* __restrict__ sums8) {
   // grid (ceil(C8*2 / 32), B), block (32, PARTS): thread (col, part) sums a contiguous row range
-  constexpr int PARTS = 8;
   __shared__ double sm[PARTS][32];
   const int b = blockIdx.y;
   const int col = blockIdx.x * 32 + threadIdx.x;  // index into [C8][2]
@@ -349,7 +430,16 @@ __global__ void sums8_reduce_kernel(const float* __restrict__ partial, int R, in
   double acc = 0.0;
   if (col < C8 * 2) {
     const float* p = partial + ((size_t)b * R) * (C8 * 2) + col;
-    for (int r = r0; r < r1; ++r) acc += (double)p[(size_t)r * (C8 * 2)];
+    int r = r0;
+    for (; r + 4 <= r1; r += 4) {  // 4 independent loads in flight, summed in row order
+      const float v0 = p[(size_t)r * (C8 * 2)], v1 = p[(size_t)(r + 1) * (C8 * 2)];
+      const float v2 = p[(size_t)(r + 2) * (C8 * 2)], v3 = p[(size_t)(r + 3) * (C8 * 2)];
+      acc += (double)v0;
+      acc += (double)v1;
+      acc += (double)v2;
+      acc += (double)v3;
+    }
+    for (; r < r1; ++r) acc += (double)p[(size_t)r * (C8 * 2)];
   }
   sm[part][threadIdx.x] = acc;
   __syncthreads();
@@ -364,7 +454,12 @@ __global__ void sums8_reduce_kernel(const float* __restrict__ partial, int R, in
 int sums8_reduce_launch(const float* partial, int B, int R, int C, double* sums8,
                         cudaStream_t stream) {
   const int C8 = C / 8;
-  sums8_reduce_kernel<<<dim3(cdiv(C8 * 2, 32), B), dim3(32, 8), 0, stream>>>(partial, R, C8, sums8);
+  // the split depends on R (the image size) only, never on the batch: a chain's bits are the
+  // same whatever batch it runs in
+  if (R >= 256)
+    sums8_reduce_kernel<32><<<dim3(cdiv(C8 * 2, 32), B), dim3(32, 32), 0, stream>>>(partial, R, C8, sums8);
+  else
+    sums8_reduce_kernel<8><<<dim3(cdiv(C8 * 2, 32), B), dim3(32, 8), 0, stream>>>(partial, R, C8, sums8);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;
@@ -646,15 +741,19 @@ static constexpr int HEAD_CC = 16;
 static constexpr int HEAD_TW = 32, HEAD_TH = 16;
 static constexpr int HEAD_THREADS = 128;  // 16 rows x 8 groups of 4 pixels
 
+// NO = number of output channels computed: 3 (the sampler keeps only eps, diffusion.py:529-530)
+// or 6
+template <int NO>
 __global__ void __launch_bounds__(HEAD_THREADS)
 head_kernel(const __half* __restrict__ h, const float* __restrict__ stats,
             const float* __restrict__ gamma, const float* __restrict__ beta,
             const float* __restrict__ w, const float* __restrict__ bias, int B, int H, int W,
             int C, int n_out, float* __restrict__ out, int out_channels_total) {
   // w: [n_out_total(6)][C][3][3] fp32 (PyTorch layout); only the first n_out rows are used
-  constexpr int PW = HEAD_TW + 2, PH = HEAD_TH + 2;
-  __shared__ float s_act[HEAD_CC * PH * PW];
-  __shared__ float s_w[9 * HEAD_CC * 8];  // [tap][cc][8 padded outputs]
+  constexpr int PW = HEAD_TW + 4, PH = HEAD_TH + 2;  // rows padded to 36 floats: aligned float4
+  constexpr int WP = NO <= 4 ? 4 : 8;                // padded outputs per (tap, channel)
+  __shared__ __align__(16) float s_act[HEAD_CC * PH * PW];
+  __shared__ __align__(16) float s_w[9 * HEAD_CC * WP];  // [tap][cc][WP padded outputs]
   __shared__ float s_ab[2 * HEAD_CC];     // GroupNorm affine of the chunk's channels
   const int tiles_x = W / HEAD_TW, tiles_y = H / HEAD_TH;
   const int tile = blockIdx.x;
@@ -663,11 +762,11 @@ head_kernel(const __half* __restrict__ h, const float* __restrict__ stats,
   const int tid = threadIdx.x;
   const int row = tid / 8, col4 = (tid % 8) * 4;
   const int cpg = C / 32;
-  float acc[4][6];
+  float acc[4][NO];
 #pragma unroll
   for (int p = 0; p < 4; ++p)
 #pragma unroll
-    for (int o = 0; o < 6; ++o) acc[p][o] = 0.f;
+    for (int o = 0; o < NO; ++o) acc[p][o] = 0.f;
 
   for (int cb = 0; cb < C; cb += HEAD_CC) {
     __syncthreads();
@@ -679,16 +778,17 @@ head_kernel(const __half* __restrict__ h, const float* __restrict__ stats,
       s_ab[tid] = a;
       s_ab[HEAD_CC + tid] = beta[c] - mean * a;
     }
-    for (int i = tid; i < 9 * HEAD_CC * 8; i += HEAD_THREADS) {
-      const int o = i % 8, cc = (i / 8) % HEAD_CC, tap = i / (8 * HEAD_CC);
+    for (int i = tid; i < 9 * HEAD_CC * WP; i += HEAD_THREADS) {
+      const int o = i % WP, cc = (i / WP) % HEAD_CC, tap = i / (WP * HEAD_CC);
       s_w[i] = o < n_out ? w[((size_t)o * C + cb + cc) * 9 + tap] : 0.f;
     }
     __syncthreads();
     // stage normalised + SiLU activations (zero outside the image = conv zero padding)
-    for (int i = tid; i < PH * PW * (HEAD_CC / 8); i += HEAD_THREADS) {
+    for (int i = tid; i < PH * (HEAD_TW + 2) * (HEAD_CC / 8); i += HEAD_THREADS) {
       const int c8 = i % (HEAD_CC / 8);
-      const int pp = i / (HEAD_CC / 8);
-      const int px = pp % PW, py = pp / PW;
+      const int pq = i / (HEAD_CC / 8);
+      const int px = pq % (HEAD_TW + 2), py = pq / (HEAD_TW + 2);
+      const int pp = py * PW + px;
       const int yy = y0 + py - 1, xx = x0 + px - 1;
       float v[8];
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
@@ -710,29 +810,29 @@ head_kernel(const __half* __restrict__ h, const float* __restrict__ stats,
       const float* sa = s_act + cc * PH * PW;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
-        float a6[6];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) a6[j] = sa[(row + ky) * PW + col4 + j];
+        const float4 a03 = *(const float4*)(sa + (row + ky) * PW + col4);
+        const float2 a45 = *(const float2*)(sa + (row + ky) * PW + col4 + 4);
+        const float a6[6] = {a03.x, a03.y, a03.z, a03.w, a45.x, a45.y};
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float4 w0 = *(const float4*)(s_w + ((ky * 3 + kx) * HEAD_CC + cc) * 8);
-          const float4 w1 = *(const float4*)(s_w + ((ky * 3 + kx) * HEAD_CC + cc) * 8 + 4);
+          const float4 w0 = *(const float4*)(s_w + ((ky * 3 + kx) * HEAD_CC + cc) * WP);
+          float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (NO > 4) w1 = *(const float4*)(s_w + ((ky * 3 + kx) * HEAD_CC + cc) * WP + WP - 4);
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const float av = a6[p + kx];
-            acc[p][0] += av * w0.x;
-            acc[p][1] += av * w0.y;
-            acc[p][2] += av * w0.z;
-            acc[p][3] += av * w0.w;
-            acc[p][4] += av * w1.x;
-            acc[p][5] += av * w1.y;
+#pragma unroll
+            for (int o = 0; o < NO; ++o) acc[p][o] += av * wv[o];
           }
         }
       }
     }
   }
   const int y = y0 + row;
-  for (int o = 0; o < n_out; ++o) {
+#pragma unroll
+  for (int o = 0; o < NO; ++o) {
+    if (o >= n_out) break;
     float4 r = make_float4(acc[0][o] + bias[o], acc[1][o] + bias[o], acc[2][o] + bias[o],
                            acc[3][o] + bias[o]);
     *(float4*)(out + (((size_t)b * out_channels_total + o) * H + y) * W + x0 + col4) = r;
@@ -746,8 +846,12 @@ int head_launch(const __half* h, const float* stats, const float* gamma, const f
                 W, HEAD_TH, HEAD_TW);
   PDR_CHECK_ARG(C % HEAD_CC == 0 && C % 32 == 0 && n_out >= 1 && n_out <= 6, "head: bad channels");
   const int tiles = B * (H / HEAD_TH) * (W / HEAD_TW);
-  head_kernel<<<tiles, HEAD_THREADS, 0, stream>>>(h, stats, gamma, beta, w, bias, B, H, W, C, n_out, out,
-                                        out_channels_total);
+  if (n_out <= 3)
+    head_kernel<3><<<tiles, HEAD_THREADS, 0, stream>>>(h, stats, gamma, beta, w, bias, B, H, W, C,
+                                                       n_out, out, out_channels_total);
+  else
+    head_kernel<6><<<tiles, HEAD_THREADS, 0, stream>>>(h, stats, gamma, beta, w, bias, B, H, W, C,
+                                                       n_out, out, out_channels_total);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;

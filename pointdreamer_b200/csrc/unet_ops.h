@@ -39,7 +39,9 @@ int head_launch(const __half* h, const float* stats, const float* gamma, const f
                 float* out, int out_channels_total, cudaStream_t stream);
 
 // qkv [B,T,3C] (legacy head-major layout) -> a [B,T,C]; head dim 64
-int attention_launch(const __half* qkv, int B, int T, int heads, __half* out, cudaStream_t stream);
+// prescaled != 0: q and k were already multiplied by 64^-1/4 (fp16) by the qkv conv's epilogue
+int attention_launch(const __half* qkv, int B, int T, int heads, int prescaled, __half* out,
+                     cudaStream_t stream);
 
 // ---- DDNM sampler ----
 struct DdnmStepCoef {
