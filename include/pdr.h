@@ -229,6 +229,63 @@ int pdr_unproject(const float* images, int res, const float* cam_params, int V, 
 /* number of set bytes in mask[n]; synchronises `stream`. ws_counter: int[1] device scratch */
 int pdr_mask_count(const uint8_t* mask, size_t n, int* ws_counter, int* out_host, void* stream);
 
+/* ------------------------------------- "next" rows: atlas inputs (N4), optimiser (N1) --- */
+/* Attribute interpolation over a rasterised mesh.  Replaces nvdiffrast.torch.interpolate as used
+ * at models/get3d/extract_texture_map.py:60 (gb_pos per atlas texel) and ours_utils.py:1697
+ * (texture uv per view pixel).  Canonical rule (nvdiffrast's scheme): fp32 barycentrics u = eA/(eA+eB+eC),
+ * v = eB/(eA+eB+eC) from the rasteriser's exact integer edge functions, then
+ * (u*a0 + v*a1) + ((1-u)-v)*a2 (oracle/project.py:interpolate).
+ *   pos [V,Vm,4] fp32 and faces [F,3] int32: what pdr_rasterize was called with ;
+ *   face_idx [V,res,res] int64 from pdr_rasterize ; attr [Na,C] fp32 (C = 2 or 3) ;
+ *   attr_faces [F,3] int32 (attribute index triple per face) ; flip_y != 0: output row y is
+ *   raster row res-1-y (torch.flip(..,[1]), ours_utils.py:1702-1705)
+ *   out [V,res,res,C] fp32 (0 where empty) ; mask_out [V,res,res] u8 or NULL (same flip) */
+int pdr_interpolate(const float* pos, const int* faces, const long long* face_idx,
+                    const float* attr, const int* attr_faces, int V, int Vm, int res, int C,
+                    int flip_y, float* out, uint8_t* mask_out, void* stream);
+/* Unit face normals.  Replaces kal.ops.mesh.face_normals(face_vertices, unit=True), demo.py:422.
+ *   vertices [Vm,3] fp32 ; faces [F,3] int32 ; out [F,3] fp32 */
+int pdr_face_normals(const float* vertices, const int* faces, int F, float* out, void* stream);
+/* Per-view clip-space vertices of optimize_color (ours_utils.py:1676-1693): camera transform,
+ * then ((uv - c)/s) * (1 - 2*padding) * inpaint_scale + 0.5, clip [0,1], *2-1.
+ *   cam_params [V,16] ; vertices [Vm,3] ; uv_centers [V,2] ; uv_scales [V] ; inpaint_scales [V]
+ *   pos [V,Vm,4] fp32 (x, y, NDC z, 1) */
+int pdr_project_fixed(const float* cam_params, const float* vertices, int Vm, int V,
+                      double padding, const float* uv_centers, const float* uv_scales,
+                      const float* inpaint_scales, float* pos, void* stream);
+
+/* Texture optimiser.  Replaces optimize_color, ours_utils.py:1583-1785 (100 Adam iterations of
+ * an L1 fit of the atlas' float64 bilinear renders to the inpainted views; kaolin
+ * texture_mapping == F.grid_sample(align_corners=False, padding_mode='border'), y reversed).
+ * The atlas is the [3,R,R] planar fp32 parameter in the frame optimize_color receives it
+ * (demo.py:217: permute(2,0,1).flip(1)).  Call order: prepare -> (host: sort keys, count keys
+ * != INT64_MAX) -> build -> (host: seg_start = indices where head == 1, then n_valid appended)
+ * -> iterations x (forward, step).
+ *   prepare: uv_map [V,res,res,2] fp32 and mask [V,res,res] u8 in the FLIPPED frame
+ *            (pdr_interpolate with flip_y=1) ; vis [V,R,R] u8 shrinked visibility or NULL ;
+ *            inpainted [V,3,r0,r0] fp32 (bilinearly resized to res like transforms.Resize) ->
+ *            active [V,res,res] u8 ; target [V,res,res,3] fp32 ; keys int64[V*res*res*4]
+ *            (texel << 32 | (pixel*4 + corner), INT64_MAX = no contribution)
+ *   build:   sorted keys -> entry_pix u32[n_valid], entry_w f64[n_valid], head u8[n_valid]
+ *   forward: signs int8[V*res*res*4] (zero-initialised by the caller) ; images f64 [V,3,res,res]
+ *            or NULL (the reference's second return value)
+ *   step:    gradient gather + one Adam update of the touched texels; m, v: fp32 [3,R,R] state;
+ *            lerp_w = 1-beta1, bc2_sqrt = sqrt(1-beta2^t), neg_step_size = -lr_t/(1-beta1^t)
+ *            (torch.optim.Adam's foreach formulas) */
+int pdr_texopt_prepare(const float* uv_map, const uint8_t* mask, const uint8_t* vis,
+                       const float* inpainted, int r0, int V, int res, int R, uint8_t* active,
+                       float* target, long long* keys, void* stream);
+int pdr_texopt_build(const long long* sorted_keys, long long n_valid, const float* uv_map, int R,
+                     unsigned int* entry_pix, double* entry_w, uint8_t* head, void* stream);
+int pdr_texopt_forward(const float* atlas, const float* uv_map, const uint8_t* active,
+                       const float* target, int V, int res, int R, signed char* signs,
+                       double* images, void* stream);
+int pdr_texopt_step(float* atlas, float* m, float* v, const long long* sorted_keys,
+                    const long long* seg_start, long long n_seg, const unsigned int* entry_pix,
+                    const double* entry_w, const signed char* signs, int V, int res, int R,
+                    float lerp_w, float beta2, float one_minus_beta2, float bc2_sqrt, float eps,
+                    float neg_step_size, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,7 +85,7 @@ def _edge_inclusive(dx, dy):
     return (dy > 0) or (dy == 0 and dx < 0)
 
 
-def rasterize(pos, faces, res):
+def rasterize(pos, faces, res, return_bary=False):
     """Canonical z-buffer rasteriser.
 
       * vertex xy snapped to a 1/256-pixel grid; sample point = pixel centre (col+0.5,row+0.5);
@@ -97,13 +97,16 @@ def rasterize(pos, faces, res):
       * nearest depth wins, equal depth -> lowest triangle index.
 
     pos [V,Vm,4] fp32 (w == 1), faces [F,3] int.  Returns depth[V,res,res] fp32 (0 empty),
-    face_idx[V,res,res] int64 (-1 empty), mask[V,res,res] bool.
+    face_idx[V,res,res] int64 (-1 empty), mask[V,res,res] bool; with return_bary also the fp32
+    barycentrics bary[V,res,res,2] = (eA/tot, eB/tot) of the winning triangle's vertices 0 and 1
+    (nvdiffrast's rast[..., 0:2]; 0 where empty).
     """
     V = pos.shape[0]
     faces = np.asarray(faces, dtype=np.int64)
     depth = np.zeros((V, res, res), dtype=F32)
     fidx = -np.ones((V, res, res), dtype=np.int64)
     zbuf = np.full((V, res, res), np.inf, dtype=F32)
+    bary = np.zeros((V, res, res, 2), dtype=F32) if return_bary else None
     for v in range(V):
         X = _snap(pos[v, :, 0], res)
         Y = _snap(pos[v, :, 1], res)
@@ -142,9 +145,31 @@ def rasterize(pos, faces, res):
             win = ok & ((z < zb) | ((z == zb) & (f < fb)))
             zb[win] = z[win]
             fb[win] = f
+            if return_bary:
+                bb = bary[v, ymin:ymax + 1, xmin:xmax + 1]
+                bb[win, 0] = (wa / tot)[win]
+                bb[win, 1] = (wb / tot)[win]
     mask = fidx >= 0
     depth[mask] = zbuf[mask]
+    if return_bary:
+        return depth, fidx, mask, bary
     return depth, fidx, mask
+
+
+def interpolate(bary, fidx, attr, attr_faces):
+    """nvdiffrast.torch.interpolate (call sites models/get3d/extract_texture_map.py:60,
+    ours_utils.py:1705), canonical fp32 rule: out = (u*a0 + v*a1) + ((1 - u) - v)*a2 with (u, v)
+    the rasteriser's barycentrics; 0 where the pixel is empty.
+    bary [V,H,W,2] fp32, fidx [V,H,W] int64, attr [Na,C] fp32, attr_faces [F,3] int."""
+    attr = np.asarray(attr, dtype=F32)
+    attr_faces = np.asarray(attr_faces, dtype=np.int64)
+    hit = fidx >= 0
+    f = np.where(hit, fidx, 0)
+    a0, a1, a2 = attr[attr_faces[f, 0]], attr[attr_faces[f, 1]], attr[attr_faces[f, 2]]
+    u, v = bary[..., 0:1], bary[..., 1:2]
+    b2 = (F32(1) - u) - v
+    out = (u * a0 + v * a1) + b2 * a2
+    return np.where(hit[..., None], out, F32(0)).astype(F32)
 
 
 def resize_mask_half_any(mask, res):

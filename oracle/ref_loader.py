@@ -12,7 +12,10 @@ arithmetic calls the hot path makes are replaced by shims that implement the can
 documented in oracle/camera.py and oracle/project.py:
    kaolin.render.camera.Camera            -> TorchCamera (same fp32 op order as oracle.camera)
    kaolin.metrics.pointcloud.sided_distance -> exact argmin, lowest index on ties
-   nvdiffrast.torch.rasterize             -> oracle.project.rasterize
+   nvdiffrast.torch.rasterize / interpolate -> oracle.project.rasterize / interpolate
+   kaolin.render.mesh.texture_mapping     -> F.grid_sample (kaolin's published bilinear branch)
+   kaolin.ops.mesh.face_normals           -> normalised cross product
+   xatlas.parametrize                     -> result supplied by the test (third-party, absent)
    open3d ... hidden_point_removal        -> scipy ConvexHull on the spherically flipped cloud
 """
 import contextlib
@@ -112,13 +115,81 @@ def _rasterize(glctx, pos, tri, resolution, grad_db=False):
     import torch
 
     from . import project as oproj
-    depth, fidx, mask = oproj.rasterize(pos.detach().cpu().numpy(), tri.cpu().numpy(),
-                                        int(resolution[0]))
+    depth, fidx, mask, bary = oproj.rasterize(pos.detach().cpu().numpy(), tri.cpu().numpy(),
+                                              int(resolution[0]), return_bary=True)
     V, H, W = depth.shape
     rast = np.zeros((V, H, W, 4), dtype=np.float32)
+    rast[..., 0:2] = bary
     rast[..., 2] = depth
     rast[..., 3] = (fidx + 1).astype(np.float32)
     return torch.from_numpy(rast), None
+
+
+def _interpolate(attr, rast, tri, rast_db=None, diff_attrs=None):
+    """nvdiffrast.torch.interpolate shim -> oracle.project.interpolate (barycentrics from
+    rast[..., 0:2], triangle id + 1 in rast[..., 3])."""
+    import torch
+
+    from . import project as oproj
+    a = attr.detach().cpu().numpy()
+    if a.ndim == 3:
+        a = a[0]
+    r = rast.detach().cpu().numpy()
+    fidx = r[..., 3].astype(np.int64) - 1
+    out = oproj.interpolate(np.ascontiguousarray(r[..., 0:2]), fidx, a, tri.cpu().numpy())
+    return torch.from_numpy(out), None
+
+
+def _texture_mapping(texture_coordinates, texture_maps, mode="nearest"):
+    """kaolin 0.15.0 render.mesh.texture_mapping, bilinear branch (published algorithm;
+    call site ours_utils.py:1721)."""
+    if mode != "bilinear":
+        raise NotImplementedError("texture_mapping shim: bilinear only")
+    from . import optimize as oopt
+    return oopt.texture_mapping_bilinear(texture_coordinates, texture_maps)
+
+
+def _face_normals(face_vertices, unit=False):
+    import torch
+    v0, v1, v2 = face_vertices[..., 0, :], face_vertices[..., 1, :], face_vertices[..., 2, :]
+    n = torch.cross(v1 - v0, v2 - v0, dim=-1)
+    if unit:
+        n = torch.nn.functional.normalize(n, dim=-1)
+    return n
+
+
+_xatlas_result = None
+
+
+def set_xatlas_parametrization(vmapping, indices, uvs):
+    """xatlas.parametrize is third-party (and absent): tests supply its result."""
+    global _xatlas_result
+    _xatlas_result = (np.asarray(vmapping), np.asarray(indices), np.asarray(uvs))
+
+
+def _xatlas_parametrize(vertices, faces):
+    if _xatlas_result is None:
+        raise RuntimeError("xatlas shim: call set_xatlas_parametrization first")
+    return _xatlas_result
+
+
+@contextlib.contextmanager
+def cuda_literals_to_cpu():
+    """optimize_color hard-codes device='cuda' in one torch.ones call (ours_utils.py:1670) whose
+    result is never used on the nvdiffrast branch; let it run on a CPU-only machine."""
+    import torch
+    orig = torch.ones
+
+    def ones(*a, **k):
+        if k.get("device") == "cuda" and not torch.cuda.is_available():
+            k["device"] = "cpu"
+        return orig(*a, **k)
+
+    torch.ones = ones
+    try:
+        yield
+    finally:
+        torch.ones = orig
 
 
 class _Dummy:
@@ -193,6 +264,17 @@ def install_stubs():
     sys.modules["kaolin.render.camera"].Camera = _make_torch_camera()
     sys.modules["kaolin.metrics.pointcloud"].sided_distance = _sided_distance
     sys.modules["nvdiffrast.torch"].rasterize = _rasterize
+    sys.modules["nvdiffrast.torch"].interpolate = _interpolate
+    import torch as _torch
+    krm = sys.modules["kaolin.render.mesh"]
+    krm.texture_mapping = _texture_mapping
+    krm.prepare_vertices = lambda *a, **k: (None, None, None)  # result unused (ours_utils.py:1655)
+    krc = sys.modules["kaolin.render.camera"]
+    krc.generate_transformation_matrix = lambda *a, **k: _torch.zeros(1)   # results unused
+    krc.generate_perspective_projection = lambda *a, **k: _torch.zeros(3, 1)
+    krc.perspective_camera = lambda *a, **k: None
+    sys.modules["kaolin.ops.mesh"].face_normals = _face_normals
+    sys.modules["xatlas"].parametrize = _xatlas_parametrize
     sys.modules["nvdiffrast.torch"].RasterizeCudaContext = lambda *a, **k: None
     o3d = sys.modules["open3d"]
     o3d.geometry = types.SimpleNamespace(PointCloud=_O3dPointCloud)

@@ -236,4 +236,58 @@ int pdr_mask_count(const uint8_t* mask, size_t n, int* ws_counter, int* out_host
   return mask_count_sync(mask, n, ws_counter, out_host, (cudaStream_t)stream);
 }
 
+int pdr_interpolate(const float* pos, const int* faces, const long long* face_idx,
+                    const float* attr, const int* attr_faces, int V, int Vm, int res, int C,
+                    int flip_y, float* out, uint8_t* mask_out, void* stream) {
+  PDR_CHECK_ARG(pos && faces && face_idx && attr && attr_faces && out,
+                "pdr_interpolate: null pointer");
+  return interpolate_launch(pos, faces, face_idx, attr, attr_faces, V, Vm, res, C, flip_y, out,
+                            mask_out, (cudaStream_t)stream);
+}
+int pdr_face_normals(const float* vertices, const int* faces, int F, float* out, void* stream) {
+  PDR_CHECK_ARG(vertices && faces && out, "pdr_face_normals: null pointer");
+  return face_normals_launch(vertices, faces, F, out, (cudaStream_t)stream);
+}
+int pdr_project_fixed(const float* cam_params, const float* vertices, int Vm, int V,
+                      double padding, const float* uv_centers, const float* uv_scales,
+                      const float* inpaint_scales, float* pos, void* stream) {
+  PDR_CHECK_ARG(cam_params && vertices && uv_centers && uv_scales && inpaint_scales && pos,
+                "pdr_project_fixed: null pointer");
+  return project_fixed_launch(cam_params, vertices, Vm, V, padding, uv_centers, uv_scales,
+                              inpaint_scales, pos, (cudaStream_t)stream);
+}
+int pdr_texopt_prepare(const float* uv_map, const uint8_t* mask, const uint8_t* vis,
+                       const float* inpainted, int r0, int V, int res, int R, uint8_t* active,
+                       float* target, long long* keys, void* stream) {
+  PDR_CHECK_ARG(uv_map && mask && inpainted && active && target && keys,
+                "pdr_texopt_prepare: null pointer");
+  return texopt_prepare_launch(uv_map, mask, vis, inpainted, r0, V, res, R, active, target, keys,
+                               (cudaStream_t)stream);
+}
+int pdr_texopt_build(const long long* sorted_keys, long long n_valid, const float* uv_map, int R,
+                     unsigned int* entry_pix, double* entry_w, uint8_t* head, void* stream) {
+  PDR_CHECK_ARG(sorted_keys && uv_map && entry_pix && entry_w && head,
+                "pdr_texopt_build: null pointer");
+  return texopt_build_launch(sorted_keys, n_valid, uv_map, R, entry_pix, entry_w, head,
+                             (cudaStream_t)stream);
+}
+int pdr_texopt_forward(const float* atlas, const float* uv_map, const uint8_t* active,
+                       const float* target, int V, int res, int R, signed char* signs,
+                       double* images, void* stream) {
+  PDR_CHECK_ARG(atlas && uv_map && active && target && signs, "pdr_texopt_forward: null pointer");
+  return texopt_forward_launch(atlas, uv_map, active, target, V, res, R, signs, images,
+                               (cudaStream_t)stream);
+}
+int pdr_texopt_step(float* atlas, float* m, float* v, const long long* sorted_keys,
+                    const long long* seg_start, long long n_seg, const unsigned int* entry_pix,
+                    const double* entry_w, const signed char* signs, int V, int res, int R,
+                    float lerp_w, float beta2, float one_minus_beta2, float bc2_sqrt, float eps,
+                    float neg_step_size, void* stream) {
+  PDR_CHECK_ARG(atlas && m && v && sorted_keys && seg_start && entry_pix && entry_w && signs,
+                "pdr_texopt_step: null pointer");
+  return texopt_step_launch(atlas, m, v, sorted_keys, seg_start, n_seg, entry_pix, entry_w, signs,
+                            V, res, R, lerp_w, beta2, one_minus_beta2, bc2_sqrt, eps,
+                            neg_step_size, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -49,6 +49,30 @@ size_t hpr_workspace_bytes(int V, int N);
 int hpr_launch(const float* points, int N, int V, const double* frames_dev, double radius,
                void* workspace, uint8_t* vis, cudaStream_t stream);
 
+int interpolate_launch(const float* pos, const int* faces, const long long* face_idx,
+                       const float* attr, const int* attr_faces, int V, int Vm, int res, int C,
+                       int flip_y, float* out, uint8_t* mask_out, cudaStream_t stream);
+int face_normals_launch(const float* verts, const int* faces, int F, float* out,
+                        cudaStream_t stream);
+int project_fixed_launch(const float* cams, const float* vertices, int Vm, int V, double padding,
+                         const float* centers, const float* scales, const float* inpaint_scales,
+                         float* pos, cudaStream_t stream);
+
+int texopt_prepare_launch(const float* uv_map, const uint8_t* mask, const uint8_t* vis,
+                          const float* inpainted, int r0, int V, int res, int R, uint8_t* active,
+                          float* target, long long* keys, cudaStream_t stream);
+int texopt_build_launch(const long long* sorted_keys, long long n_valid, const float* uv_map, int R,
+                        unsigned int* entry_pix, double* entry_w, uint8_t* head,
+                        cudaStream_t stream);
+int texopt_forward_launch(const float* atlas, const float* uv_map, const uint8_t* active,
+                          const float* target, int V, int res, int R, signed char* signs,
+                          double* images, cudaStream_t stream);
+int texopt_step_launch(float* atlas, float* m, float* v, const long long* sorted_keys,
+                       const long long* seg_start, long long n_seg, const unsigned int* entry_pix,
+                       const double* entry_w, const signed char* signs, int V, int res, int R,
+                       float lerp_w, float beta2, float one_m_beta2, float bc2_sqrt, float eps,
+                       float neg_step_size, cudaStream_t stream);
+
 int mask_count_sync(const uint8_t* mask, size_t n, int* ws_counter, int* out_host,
                     cudaStream_t stream);
 

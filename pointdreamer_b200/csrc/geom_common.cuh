@@ -48,4 +48,19 @@ __device__ __forceinline__ long long clipll(long long x, long long lo, long long
   return x < lo ? lo : (x > hi ? hi : x);
 }
 
+// ---- rasteriser conventions shared by rasterize / interpolate (oracle/project.py:rasterize) ----
+static constexpr int SUBPIX = 256;  // vertex xy snapped to a 1/256-pixel grid
+
+__device__ __forceinline__ long long snap_coord(float ndc, int res) {
+  const float s = ((ndc + 1.0f) * 0.5f) * (float)res;
+  return (long long)floorf(s * (float)SUBPIX + 0.5f);
+}
+__device__ __forceinline__ bool edge_inclusive(long long dx, long long dy) {
+  return (dy > 0) || (dy == 0 && dx < 0);
+}
+__device__ __forceinline__ long long floordiv(long long a, long long b) {
+  long long q = a / b;
+  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
 }  // namespace pdr

@@ -136,19 +136,7 @@ int project_launch(const float* cams, const float* vertices, int Vm, const float
 }
 
 // ------------------------------------------------------------------ K2 ----
-static constexpr int SUBPIX = 256;
-
-__device__ __forceinline__ long long snap_coord(float ndc, int res) {
-  const float s = ((ndc + 1.0f) * 0.5f) * (float)res;
-  return (long long)floorf(s * (float)SUBPIX + 0.5f);
-}
-__device__ __forceinline__ bool edge_inclusive(long long dx, long long dy) {
-  return (dy > 0) || (dy == 0 && dx < 0);
-}
-__device__ __forceinline__ long long floordiv(long long a, long long b) {
-  long long q = a / b;
-  return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
-}
+// (SUBPIX, snap_coord, edge_inclusive, floordiv: geom_common.cuh)
 
 __global__ void zkey_init_kernel(unsigned long long* keys, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

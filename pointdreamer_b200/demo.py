@@ -2,10 +2,10 @@
 plus `prepare`-style helpers to build its inputs from the reference's YAML configs.
 
 The path is project -> inpaint -> unproject.  What the reference runs AFTER the path inside the
-same function — `paint_invisible_areas_by_neighbors` (complete_unseen_by: neighbor),
-`paint_invisible_areas_by_optimize` and `optimize_color` (optimize_from) — are "next" rows
- and are not built; they can be supplied as callables (`neighbor_fill=`,
-`optimize_color=`) — e.g. the reference's own functions — otherwise asking for them raises.
+same function are "next" rows: `optimize_color` (optimize_from, N1) is built
+(ours_utils.optimize_color -> csrc/texopt.cu); `paint_invisible_areas_by_neighbors`
+(complete_unseen_by: neighbor, N2) can be supplied as a callable (`neighbor_fill=`), otherwise
+asking for it raises; `paint_invisible_areas_by_optimize` (TextureField) is out of scope.
 """
 import os
 
@@ -121,12 +121,26 @@ def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, c
                                       atlas_img, atlas_painted_mask, use_atlas=True)
         elif complete_unseen_by == 'optimize':
             raise NotImplementedError("complete_unseen_by='optimize' (TextureField) is out of scope")
+        # ---- demo.py:211-233: refine the atlas against the inpainted views ("next" row N1)
         if optimize_from is not None and optimize_from != 'None':
-            if optimize_color is None:
-                raise NotImplementedError(
-                    "optimize_from (optimize_color, ours_utils.py:1583-1785) is a 'next' row; pass "
-                    "optimize_color=<callable> or set optimize_from: None")
-            atlas_img = optimize_color(atlas_img, inpainted_images, shrinked_vis)
+            if optimize_color is not None:  # caller-supplied replacement
+                atlas_img = optimize_color(atlas_img, inpainted_images, shrinked_vis)
+            else:
+                atlas_in = atlas_img.permute(2, 0, 1).flip(1)  # [3,R,R]
+                if optimize_from == 'scratch':
+                    init_atlas, vis = None, None
+                elif optimize_from == 'naive':
+                    init_atlas, vis = atlas_in, None
+                elif optimize_from == 'ours':
+                    init_atlas, vis = atlas_in, shrinked_vis
+                else:
+                    raise ValueError(f"optimize_from={optimize_from!r}")
+                atlas_opt, _ = _ou.optimize_color(
+                    init_atlas, inpainted_images, vertices, faces, uvs, mesh_tex_idx, cams,
+                    eye_positions, None, camera_info.get('up_dirs'), uv_centers, uv_scales,
+                    padding, inpaint_scale_factors, glctx,
+                    shrinked_per_view_per_pixel_visibility=vis, return_images=False)
+                atlas_img = atlas_opt[0].flip(1).permute(1, 2, 0)  # [R,R,3]
     return vertices, uvs, faces, mesh_tex_idx, atlas_img, mask
 
 

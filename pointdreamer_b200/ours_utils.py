@@ -178,3 +178,110 @@ def get_inpainted_images(sparse_imgs, hard_mask0s, hard_mask2s, save_path, inpai
         from .io_utils import save_inpainted_pngs
         save_inpainted_pngs(inpainted, hard_mask0s, save_path, rgba=(method == 'DDNM_inpaint'))
     return inpainted
+
+
+# ------------------------------------------------------------------------------------------
+# "next" row N1: optimize_color (ours_utils.py:1583-1785)
+# ------------------------------------------------------------------------------------------
+def interpolate(attr, pos, faces, face_idx, attr_faces, flip_y=False, want_mask=False):
+    """nvdiffrast.torch.interpolate stand-in on top of `rasterize` (call sites
+    extract_texture_map.py:60, ours_utils.py:1705).  attr [Na,C] (C = 2 or 3), pos [V,Vm,4] and
+    faces [F,3] as given to `rasterize`, face_idx [V,res,res] from it, attr_faces [F,3].
+    Returns out [V,res,res,C] f32 (and the u8->bool coverage mask in the same frame)."""
+    dev = pos.device
+    V, Vm = pos.shape[0], pos.shape[1]
+    res = face_idx.shape[1]
+    C = attr.shape[-1]
+    out = torch.empty(V, res, res, C, device=dev)
+    mask = torch.empty(V, res, res, dtype=torch.uint8, device=dev) if want_mask else None
+    _lib.call("pdr_interpolate", pos.contiguous(), faces.to(torch.int32).contiguous(),
+              face_idx.contiguous(), attr.float().contiguous(),
+              attr_faces.to(torch.int32).contiguous(), V, Vm, res, C, 1 if flip_y else 0, out, mask)
+    return (out, mask.bool()) if want_mask else out
+
+
+def face_normals(vertices, faces):
+    """kal.ops.mesh.face_normals(index_vertices_by_faces(v, f), unit=True) (demo.py:421-422)."""
+    F = faces.shape[0]
+    out = torch.empty(F, 3, device=vertices.device)
+    _lib.call("pdr_face_normals", vertices.float().contiguous(),
+              faces.to(torch.int32).contiguous(), F, out)
+    return out
+
+
+def optimize_color(atlas_img, inpainted_imgs, vertices, faces, uvs, mesh_tex_idx, cams,
+                   eye_positions=None, look_ats=None, up_dirs=None, uv_centers=None,
+                   uv_scales=None, padding=0.0, inpaint_scale_factors=None, glctx=None,
+                   shrinked_per_view_per_pixel_visibility=None, lr=5e-2, iterations=100,
+                   print_every=10, res=1024, return_images=True):
+    """ours_utils.py:1583-1785, same arguments (eye_positions / look_ats / up_dirs / glctx are
+    accepted and unused, as in the reference's nvdiffrast branch; `res` is the reference's
+    hard-coded render size 1024).  atlas_img [3,R,R] (permuted + flipped by the caller,
+    demo.py:217) or None (random init, 1024^2).  Returns (atlas [1,3,R,R] f32,
+    images [V,3,res,res] f64 of the last iteration or None).
+
+    The whole optimisation runs in libpdr.so (csrc/texopt.cu): rasterise + interpolate the
+    texture uv per view pixel once, build the texel-major contribution list once, then
+    `iterations` x (forward signs, gradient gather + Adam).  torch.sort / nonzero are used once
+    for the list (setup plumbing); the Adam scalars follow torch.optim.Adam + StepLR(15, 0.5)."""
+    import math
+    dev = vertices.device
+    V = len(cams)
+    if atlas_img is not None:
+        atlas = atlas_img.detach().float().contiguous().clone()
+    else:
+        atlas = torch.rand((3, 1024, 1024), dtype=torch.float, device=dev)
+    R = atlas.shape[2]
+    if atlas.shape[1] != R:
+        raise ValueError("square atlas expected")
+    Vm = vertices.shape[0]
+    params = _camera.stack_params(cams, dev)
+    if uv_centers is None or not torch.is_tensor(uv_centers):
+        raise NotImplementedError("optimize_color needs the crop parameters of the PROJECT stage "
+                                  "(crop_img: True in every shipped config)")
+    isf = (inpaint_scale_factors if inpaint_scale_factors is not None
+           else torch.ones(V, device=dev)).float().contiguous()
+    pos = torch.empty(V, Vm, 4, device=dev)
+    _lib.call("pdr_project_fixed", params, vertices.float().contiguous(), Vm, V,
+              ctypes.c_double(float(padding)), uv_centers.float().contiguous(),
+              uv_scales.float().contiguous(), isf, pos)
+    _, face_idx, _, _ = rasterize(pos, faces, res, res)
+    uv_map, mask = interpolate(uvs, pos, faces, face_idx, mesh_tex_idx, flip_y=True, want_mask=True)
+    del face_idx
+    vis = shrinked_per_view_per_pixel_visibility
+    r0 = inpainted_imgs.shape[-1]
+    n_pix = V * res * res
+    active = torch.empty(V, res, res, dtype=torch.uint8, device=dev)
+    target = torch.empty(V, res, res, 3, device=dev)
+    keys = torch.empty(n_pix * 4, dtype=torch.int64, device=dev)
+    _lib.call("pdr_texopt_prepare", uv_map, _u8(mask).contiguous(),
+              _u8(vis).contiguous() if vis is not None else None,
+              inpainted_imgs.float().contiguous(), int(r0), V, int(res), int(R), active, target, keys)
+    keys, _ = torch.sort(keys)
+    n_valid = int((keys != torch.iinfo(torch.int64).max).sum().item())
+    keys = keys[:n_valid].contiguous()
+    entry_pix = torch.empty(max(n_valid, 1), dtype=torch.int32, device=dev)
+    entry_w = torch.empty(max(n_valid, 1), dtype=torch.float64, device=dev)
+    head = torch.zeros(max(n_valid, 1), dtype=torch.uint8, device=dev)
+    _lib.call("pdr_texopt_build", keys, ctypes.c_longlong(n_valid), uv_map, int(R), entry_pix,
+              entry_w, head)
+    seg_start = torch.nonzero(head[:n_valid]).flatten()
+    n_seg = int(seg_start.numel())
+    seg_start = torch.cat([seg_start, torch.tensor([n_valid], dtype=torch.int64, device=dev)])
+    signs = torch.zeros(n_pix * 4, dtype=torch.int8, device=dev)
+    m = torch.zeros_like(atlas)
+    v = torch.zeros_like(atlas)
+    images = torch.empty(V, 3, res, res, dtype=torch.float64, device=dev) if return_images else None
+    beta1, beta2, eps = 0.9, 0.999, 1e-8
+    for it in range(iterations):
+        last = it == iterations - 1
+        _lib.call("pdr_texopt_forward", atlas, uv_map, active, target, V, int(res), int(R), signs,
+                  images if last else None)
+        step = it + 1
+        lr_t = lr * (0.5 ** (it // 15))                      # StepLR(step_size=15, gamma=0.5)
+        bc1 = 1 - beta1 ** step
+        bc2 = 1 - beta2 ** step
+        _lib.call("pdr_texopt_step", atlas, m, v, keys, seg_start, ctypes.c_longlong(n_seg),
+                  entry_pix, entry_w, signs, V, int(res), int(R), float(1 - beta1), float(beta2),
+                  float(1 - beta2), float(math.sqrt(bc2)), float(eps), float(-(lr_t / bc1)))
+    return atlas.unsqueeze(0), images
