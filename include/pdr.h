@@ -286,6 +286,30 @@ int pdr_texopt_step(float* atlas, float* m, float* v, const long long* sorted_ke
                     float lerp_w, float beta2, float one_minus_beta2, float bc2_sqrt, float eps,
                     float neg_step_size, void* stream);
 
+/* ----------------------- "next" row N2: never-seen texels from mesh neighbours ---------- */
+/* Pieces of paint_invisible_areas_by_neighbors (unproject.py:93-196, use_atlas=True) after the
+ * host-side mesh subdivision (utils/mesh_utils.py:7-114).
+ *   vertex_colors (unproject.py:117-134): faces, face_uv_idx [F,3] int32 ; uvs [Nu,2] fp32 ;
+ *     atlas [R,R,3] fp32 ; mask [R,R] u8 (painted) ; ws_uv_idx int[Vn] scratch ->
+ *     pix int64[Vn] (row*R+col of each vertex' texel), colors [Vn,3], count [Vn] fp32 (1 = has
+ *     colour), has_color u8[Vn].  A seam vertex takes its largest uv index.
+ *   laplacian_round (unproject.py:160-163 with kaolin's uniform Laplacian as a CSR adjacency,
+ *     rowptr int[Vn+1], colidx int[nnz], neighbours ascending): every vertex with fixed == 0 gets
+ *     the count-weighted mean of its neighbours (or keeps its value); colors_out/count_out of
+ *     fixed vertices are not written (initialise both buffers alike); colored_total: device
+ *     int = number of vertices with a colour after the round.
+ *   scatter_vertex_colors (unproject.py:181-182): atlas[pix[v]] = colors[v], mask = 1; a texel
+ *     shared by several vertices takes the highest vertex index; ws_winner int[R*R] scratch. */
+int pdr_vertex_colors(const int* faces, const int* face_uv_idx, int F, const float* uvs, int Vn,
+                      const float* atlas, const uint8_t* mask, int R, int* ws_uv_idx,
+                      long long* pix, float* colors, float* count, uint8_t* has_color,
+                      void* stream);
+int pdr_laplacian_round(const int* rowptr, const int* colidx, int Vn, const uint8_t* fixed,
+                        const float* colors_in, const float* count_in, float* colors_out,
+                        float* count_out, int* colored_total, void* stream);
+int pdr_scatter_vertex_colors(const long long* pix, const float* colors, int Vn, int R,
+                              int* ws_winner, float* atlas, uint8_t* mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,8 @@ documented in oracle/camera.py and oracle/project.py:
    kaolin.render.mesh.texture_mapping     -> F.grid_sample (kaolin's published bilinear branch)
    kaolin.ops.mesh.face_normals           -> normalised cross product
    xatlas.parametrize                     -> result supplied by the test (third-party, absent)
+   kaolin.ops.mesh.uniform_laplacian      -> dense adjacency / degree (kaolin's published code)
+   trimesh.grouping.unique_rows, trimesh.geometry.faces_to_edges -> oracle.neighbors restatements
    open3d ... hidden_point_removal        -> scipy ConvexHull on the spherically flipped cloud
 """
 import contextlib
@@ -158,6 +160,21 @@ def _face_normals(face_vertices, unit=False):
     return n
 
 
+def _uniform_laplacian(num_vertices, faces):
+    """kaolin 0.15.0 ops.mesh.uniform_laplacian (published algorithm; call site
+    unproject.py:144): dense binary adjacency / vertex degree, diagonal -1, NaN -> 0."""
+    import torch
+    fwd = torch.stack([faces, torch.roll(faces, 1, dims=-1)], dim=-1)
+    bwd = torch.stack([torch.roll(faces, 1, dims=-1), faces], dim=-1)
+    ind = torch.cat([fwd, bwd], dim=1).reshape(-1, 2).unique(dim=0)
+    adj = torch.zeros(num_vertices, num_vertices)
+    adj[ind[:, 0], ind[:, 1]] = 1.0
+    L = torch.div(adj, torch.sum(adj, dim=1).view(-1, 1))
+    torch.diagonal(L)[:] = -1
+    L[torch.isnan(L)] = 0
+    return L
+
+
 _xatlas_result = None
 
 
@@ -275,6 +292,16 @@ def install_stubs():
     krc.perspective_camera = lambda *a, **k: None
     sys.modules["kaolin.ops.mesh"].face_normals = _face_normals
     sys.modules["xatlas"].parametrize = _xatlas_parametrize
+    sys.modules["kaolin.ops.mesh"].uniform_laplacian = _uniform_laplacian
+    from . import neighbors as _onb
+    for sub_name in ("trimesh.grouping", "trimesh.geometry"):
+        mod = _StubModule(sub_name)
+        mod._pdr_stub = True
+        mod.__path__ = []
+        sys.modules[sub_name] = mod
+        setattr(sys.modules["trimesh"], sub_name.split(".")[1], mod)
+    sys.modules["trimesh.grouping"].unique_rows = _onb.unique_rows      # restated trimesh
+    sys.modules["trimesh.geometry"].faces_to_edges = _onb.faces_to_edges
     sys.modules["nvdiffrast.torch"].RasterizeCudaContext = lambda *a, **k: None
     o3d = sys.modules["open3d"]
     o3d.geometry = types.SimpleNamespace(PointCloud=_O3dPointCloud)

@@ -23,7 +23,7 @@ COMMON_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", C
 # Geometry kernels must reproduce the oracle's IEEE fp32 op order bit for bit, so the
 # compiler may not contract a*b+c into an FMA there.
 NO_FMA = {"geom_project.cu", "geom_splat.cu", "geom_unproject.cu", "geom_fill.cu", "geom_hpr.cu",
-          "geom_attr.cu"}
+          "geom_attr.cu", "neighbors.cu"}
 
 
 def _nvcc():

@@ -290,4 +290,31 @@ int pdr_texopt_step(float* atlas, float* m, float* v, const long long* sorted_ke
                             neg_step_size, (cudaStream_t)stream);
 }
 
+int pdr_vertex_colors(const int* faces, const int* face_uv_idx, int F, const float* uvs, int Vn,
+                      const float* atlas, const uint8_t* mask, int R, int* ws_uv_idx,
+                      long long* pix, float* colors, float* count, uint8_t* has_color,
+                      void* stream) {
+  PDR_CHECK_ARG(faces && face_uv_idx && uvs && atlas && mask && ws_uv_idx && pix && colors &&
+                    count && has_color,
+                "pdr_vertex_colors: null pointer");
+  return vertex_colors_launch(faces, face_uv_idx, F, uvs, Vn, atlas, mask, R, ws_uv_idx, pix,
+                              colors, count, has_color, (cudaStream_t)stream);
+}
+int pdr_laplacian_round(const int* rowptr, const int* colidx, int Vn, const uint8_t* fixed,
+                        const float* colors_in, const float* count_in, float* colors_out,
+                        float* count_out, int* colored_total, void* stream) {
+  PDR_CHECK_ARG(rowptr && colidx && fixed && colors_in && count_in && colors_out && count_out &&
+                    colored_total,
+                "pdr_laplacian_round: null pointer");
+  return laplacian_round_launch(rowptr, colidx, Vn, fixed, colors_in, count_in, colors_out,
+                                count_out, colored_total, (cudaStream_t)stream);
+}
+int pdr_scatter_vertex_colors(const long long* pix, const float* colors, int Vn, int R,
+                              int* ws_winner, float* atlas, uint8_t* mask, void* stream) {
+  PDR_CHECK_ARG(pix && colors && ws_winner && atlas && mask,
+                "pdr_scatter_vertex_colors: null pointer");
+  return scatter_vertex_colors_launch(pix, colors, Vn, R, ws_winner, atlas, mask,
+                                      (cudaStream_t)stream);
+}
+
 }  // extern "C"

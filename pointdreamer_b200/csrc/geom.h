@@ -73,6 +73,17 @@ int texopt_step_launch(float* atlas, float* m, float* v, const long long* sorted
                        float lerp_w, float beta2, float one_m_beta2, float bc2_sqrt, float eps,
                        float neg_step_size, cudaStream_t stream);
 
+int vertex_colors_launch(const int* faces, const int* face_uv_idx, int F, const float* uvs, int Vn,
+                         const float* atlas, const uint8_t* mask, int R, int* ws_uv_idx,
+                         long long* pix, float* colors, float* count, uint8_t* has_color,
+                         cudaStream_t stream);
+int laplacian_round_launch(const int* rowptr, const int* colidx, int Vn, const uint8_t* fixed,
+                           const float* colors_in, const float* count_in, float* colors_out,
+                           float* count_out, int* colored_total, cudaStream_t stream);
+int scatter_vertex_colors_launch(const long long* pix, const float* colors, int Vn, int R,
+                                 int* ws_winner, float* atlas, uint8_t* mask,
+                                 cudaStream_t stream);
+
 int mask_count_sync(const uint8_t* mask, size_t n, int* ws_counter, int* out_host,
                     cudaStream_t stream);
 

@@ -3,9 +3,10 @@ plus `prepare`-style helpers to build its inputs from the reference's YAML confi
 
 The path is project -> inpaint -> unproject.  What the reference runs AFTER the path inside the
 same function are "next" rows: `optimize_color` (optimize_from, N1) is built
-(ours_utils.optimize_color -> csrc/texopt.cu); `paint_invisible_areas_by_neighbors`
-(complete_unseen_by: neighbor, N2) can be supplied as a callable (`neighbor_fill=`), otherwise
-asking for it raises; `paint_invisible_areas_by_optimize` (TextureField) is out of scope.
+(ours_utils.optimize_color -> csrc/texopt.cu) and so is `paint_invisible_areas_by_neighbors`
+(complete_unseen_by: neighbor, N2; unproject.paint_invisible_areas_by_neighbors ->
+csrc/neighbors.cu); both can be overridden with callables (`neighbor_fill=`, `optimize_color=`).
+`paint_invisible_areas_by_optimize` (TextureField network) is out of scope.
 """
 import os
 
@@ -111,10 +112,7 @@ def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, c
             atlas_img = _un.dilate_atlas(atlas_img, mask)
         elif complete_unseen_by == 'neighbor':
             if neighbor_fill is None:
-                raise NotImplementedError(
-                    "complete_unseen_by='neighbor' (paint_invisible_areas_by_neighbors, "
-                    "unproject.py:93-196) is a 'next' row; pass neighbor_fill=<callable> or use "
-                    "complete_unseen_by='unproject' / None")
+                neighbor_fill = _un.paint_invisible_areas_by_neighbors
             to_inpaint_face_id = per_atlas_pixel_face_id[0][torch.logical_not(atlas_painted_mask)].unique()
             to_inpaint_face_id = to_inpaint_face_id[to_inpaint_face_id > -1]
             atlas_img = neighbor_fill(vertices, faces, uvs, mesh_tex_idx, to_inpaint_face_id,

@@ -79,3 +79,68 @@ def dilate_atlas(atlas_img, mask):
     """unproject.py:480-504: nearest-fill the chart gutters.  atlas [R,R,3], mask [1,R,R,1]."""
     known = mask[..., 0] != 0  # [1,R,R]
     return nearest_fill(atlas_img[None], known, channels_last=True)[0]
+
+
+def paint_invisible_areas_by_neighbors(vertices, faces, uvs, face_uv_idx, to_inpaint_face_id,
+                                       atlas_img, atlas_inpainted_mask, use_atlas=True):
+    """unproject.py:93-196 ("next" row N2): subdivide the never-seen faces twice, give every vertex
+    the colour of its atlas texel, propagate colours from coloured to never-coloured vertices by
+    neighbour averaging until nothing changes (then the same number of smoothing rounds), write
+    the vertex colours back and nearest-fill the rest of the atlas.
+
+    atlas_img [R,R,3] f32, atlas_inpainted_mask [R,R] bool (neither is modified; the reference
+    mutates both).  Returns the atlas [R,R,3] f32 (the reference returns the same values as
+    float64), or (vertices, faces, vertex_colors) of the subdivided mesh when use_atlas=False."""
+    from .mesh_utils import subdivide_with_uv
+    dev = vertices.device
+    R = atlas_inpainted_mask.shape[1]
+    v, f = vertices.float(), faces.long()
+    uv, fuv = uvs.float(), face_uv_idx.long()
+    ids = to_inpaint_face_id.long()
+    for _ in range(2):  # the reference reuses the ORIGINAL face ids on the renumbered faces
+        v, f, uv, fuv = subdivide_with_uv(v, f, fuv, uv, face_index=ids)
+    Vn, F = v.shape[0], f.shape[0]
+    # kaolin adjacency_matrix as CSR: unique directed edges, neighbours ascending
+    r = torch.roll(f, 1, dims=-1)
+    key = torch.unique(torch.cat([(f << 32) | r, (r << 32) | f]).reshape(-1))
+    rows = key >> 32
+    rowptr = torch.zeros(Vn + 1, dtype=torch.int64, device=dev)
+    rowptr[1:] = torch.cumsum(torch.bincount(rows, minlength=Vn), 0)
+    rowptr = rowptr.to(torch.int32)
+    colidx = (key & 0xFFFFFFFF).to(torch.int32)
+
+    atlas = atlas_img.float().contiguous().clone()
+    mask = _u8(atlas_inpainted_mask).contiguous().clone()
+    pix = torch.empty(Vn, dtype=torch.int64, device=dev)
+    colors = torch.empty(Vn, 3, device=dev)
+    count = torch.empty(Vn, device=dev)
+    has = torch.empty(Vn, dtype=torch.uint8, device=dev)
+    ws = torch.empty(Vn, dtype=torch.int32, device=dev)
+    _lib.call("pdr_vertex_colors", f.to(torch.int32).contiguous(), fuv.to(torch.int32).contiguous(),
+              F, uv.contiguous(), Vn, atlas, mask, R, ws, pix, colors, count, has)
+    cur = (colors, count)
+    nxt = (colors.clone(), count.clone())
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    total = int(has.sum().item())
+    coloring_round, stage = 0, "uncolored"
+    while stage == "uncolored" or coloring_round > 0:
+        _lib.call("pdr_laplacian_round", rowptr, colidx, Vn, has, cur[0], cur[1], nxt[0], nxt[1],
+                  counter)
+        cur, nxt = nxt, cur
+        new_total = int(counter.item())
+        if new_total > total:
+            total = new_total
+            coloring_round += 1
+        else:
+            stage = "colored"
+            coloring_round -= 1
+        if coloring_round > 10000:
+            break
+    vert_colors = cur[0]
+    if torch.isnan(vert_colors).any():
+        raise RuntimeError("paint_invisible_areas_by_neighbors: NaN vertex colour")
+    if not use_atlas:
+        return v, f, vert_colors
+    winner = torch.empty(R * R, dtype=torch.int32, device=dev)
+    _lib.call("pdr_scatter_vertex_colors", pix, vert_colors, Vn, R, winner, atlas, mask)
+    return nearest_fill(atlas[None], mask[None] != 0, channels_last=True)[0]
