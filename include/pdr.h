@@ -310,6 +310,14 @@ int pdr_laplacian_round(const int* rowptr, const int* colidx, int Vn, const uint
 int pdr_scatter_vertex_colors(const long long* pix, const float* colors, int Vn, int R,
                               int* ws_winner, float* atlas, uint8_t* mask, void* stream);
 
+/* ----------------------------------- "next" row N3: output formats ---------------------- */
+/* 8-bit atlas exactly as save_textured_mesh quantises it (demo.py:283-301): img*255 in fp32,
+ * clip [0,255], truncate, rows flipped.  atlas [R,R,3] fp32 ; mask [R,R] u8 or NULL ->
+ * rgb u8 [R,R,3] (model_normalized.png) ; rgba u8 [R,R,4] or NULL (atlas_wo_background.png,
+ * alpha = mask*255). */
+int pdr_atlas_to_u8(const float* atlas, const uint8_t* mask, int R, uint8_t* rgb, uint8_t* rgba,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -317,4 +317,10 @@ int pdr_scatter_vertex_colors(const long long* pix, const float* colors, int Vn,
                                       (cudaStream_t)stream);
 }
 
+int pdr_atlas_to_u8(const float* atlas, const uint8_t* mask, int R, uint8_t* rgb, uint8_t* rgba,
+                    void* stream) {
+  PDR_CHECK_ARG(atlas && rgb, "pdr_atlas_to_u8: null pointer");
+  return atlas_to_u8_launch(atlas, mask, R, rgb, rgba, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -84,6 +84,9 @@ int scatter_vertex_colors_launch(const long long* pix, const float* colors, int 
                                  int* ws_winner, float* atlas, uint8_t* mask,
                                  cudaStream_t stream);
 
+int atlas_to_u8_launch(const float* atlas, const uint8_t* mask, int R, uint8_t* rgb, uint8_t* rgba,
+                       cudaStream_t stream);
+
 int mask_count_sync(const uint8_t* mask, size_t n, int* ws_counter, int* out_host,
                     cudaStream_t stream);
 

@@ -211,3 +211,107 @@ def colorize_from_host(scene, camera_info, cfg, inpainter, device):
     atlas_host.copy_(atlas, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return atlas_host, h2d, atlas.numel() * atlas.element_size()
+
+
+# ------------------------------------------------------------------------------------------
+# "next" row N3: the file-level flow of demo.py (recon_one_textured_mesh, 358-470) and its CLI
+# ------------------------------------------------------------------------------------------
+def recon_one_textured_mesh(cfg, inpainter, camera_info, pc_file, name, device, mesh_file=None,
+                            logger=None):
+    """demo.py:358-470 without the POCO/SPR geometry stage (out of scope): the
+    untextured mesh must exist as `<pc_file minus .ply>_untextured_mesh.obj` (the reference's own
+    load_exist_geo branch, demo.py:391-398) or be given as `mesh_file`.
+
+    Writes the reference's output tree under cfg['output_path']/name:
+      input_pc.ply, geo/xatlas_<R>.pth, others/{i}_{sparse,mask0,mask2,inpainted}.png,
+      models/model_normalized.{obj,mtl,png}, others/atlas_wo_background.png.
+    UV unwrapping: geo/xatlas_<R>.pth is reused when present (demo.py:430-438); otherwise the
+    mesh's own `vt` / `f v/vt` records are taken as the parametrisation, or xatlas is called if it
+    is installed."""
+    from . import extract_texture_map as _etm
+    from . import io_utils as _io
+    out_root = os.path.join(cfg["output_path"], name)
+    for sub in ("geo", "models", "others"):
+        os.makedirs(os.path.join(out_root, sub), exist_ok=True)
+    R = cfg["xatlas_texture_res"]
+    xatlas_save_file = os.path.join(out_root, "geo", f"xatlas_{R}.pth")
+
+    xyz_np, rgb_np = _io.read_ply_xyzrgb(pc_file)
+    if len(xyz_np) > 30000:  # demo.py:371-374
+        raise NotImplementedError(
+            f"Point number > 30000! ({len(xyz_np)} points)({pc_file}) \n Please try uniformly "
+            "subsampling the input point cloud first")
+    xyz = torch.from_numpy(xyz_np).to(device)
+    rgb = torch.from_numpy(rgb_np).float().to(device) / 255.0
+    vmin, vmax = xyz.min(0)[0], xyz.max(0)[0]
+    xyz = (xyz - (vmax + vmin) / 2.) / (vmax - vmin).max()
+    _io.save_colored_pc_ply(xyz.cpu().numpy(), rgb.cpu().numpy(), os.path.join(out_root, "input_pc.ply"))
+
+    geo = mesh_file or pc_file.replace(".ply", "_untextured_mesh.obj")
+    if not os.path.exists(geo):
+        raise NotImplementedError(
+            f"no untextured mesh at {geo}: geometry reconstruction (POCO / SPR, demo.py:399-419) is "
+            "outside this package; pass mesh_file=")
+    v_np, uv_np, f_np, ft_np = _io.loadobjtex(geo)
+    vertices = torch.from_numpy(v_np).to(device)
+    faces = torch.from_numpy(f_np).to(device)
+    vertices = (vertices - (vmax + vmin) / 2.) / (vmax - vmin).max()  # demo.py:396-397
+    f_normals = _ou.face_normals(vertices, faces)
+
+    xatlas_dict = None
+    if os.path.exists(xatlas_save_file):
+        try:
+            xatlas_dict = {k: v.to(device) for k, v in torch.load(xatlas_save_file).items()}
+        except Exception:
+            xatlas_dict = None
+    if xatlas_dict is None:
+        par = (None, ft_np.astype("uint64"), uv_np) if uv_np is not None else None
+        uvs, mesh_tex_idx, gb_pos, mask, face_id = _etm.xatlas_uvmap_w_face_id(
+            None, vertices, faces, resolution=R, parametrization=par)
+        xatlas_dict = {'uvs': uvs, 'mesh_tex_idx': mesh_tex_idx, 'gb_pos': gb_pos, 'mask': mask,
+                       'per_atlas_pixel_face_id': face_id}
+        torch.save(xatlas_dict, xatlas_save_file)
+
+    keys = {k: cfg[k] for k in PATH_CONFIG_KEYS}
+    vertices, uvs, faces, mesh_tex_idx, atlas_img, mask = colorize_one_mesh(
+        xyz, rgb, vertices, faces, f_normals, xatlas_dict, camera_info, inpainter=inpainter,
+        save_img_path=os.path.join(out_root, "others"), device=device, logger=logger, glctx=None,
+        **keys)
+    _io.save_textured_mesh(vertices, uvs, faces, mesh_tex_idx, atlas_img, mask, out_root)
+    return out_root
+
+
+def main(argv=None):
+    """python -m pointdreamer_b200.demo --config configs/default.yaml --pc_file cloud.ply
+    [--mesh_file mesh.obj] [--output_path output] [--ckpt 256x256_diffusion_uncond.pt]"""
+    import argparse
+
+    from .ddnm_inpainting import Inpainter
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument("--config", default=None, help="one of the reference's configs/*.yaml")
+    ap.add_argument("--pc_file", required=True)
+    ap.add_argument("--mesh_file", default=None)
+    ap.add_argument("--output_path", default=None)
+    ap.add_argument("--ckpt", default="models/DDNM/256x256_diffusion_uncond.pt")
+    ap.add_argument("--view_num", type=int, default=None)
+    ap.add_argument("--texture_gen_method", default=None)
+    args = ap.parse_args(argv)
+    cfg = dict(DEFAULT_CONFIG)
+    if args.config:
+        cfg.update(load_config(args.config))
+    for k in ("output_path", "view_num", "texture_gen_method"):
+        if getattr(args, k) is not None:
+            cfg[k] = getattr(args, k)
+    cfg.setdefault("output_path", "output")
+    device = torch.device("cuda:0")
+    inpainter = Inpainter(device, ckpt_path=args.ckpt) \
+        if cfg["texture_gen_method"] == "DDNM_inpaint" else None
+    camera_info = prepare_cameras(cfg, device)
+    name = os.path.basename(args.pc_file).split(".")[0]
+    out = recon_one_textured_mesh(cfg, inpainter, camera_info, args.pc_file, name, device,
+                                  mesh_file=args.mesh_file)
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()

@@ -77,3 +77,96 @@ def normalize_cloud(xyz):
     vmin, vmax = xyz.min(0), xyz.max(0)
     xyz = xyz - (vmax + vmin) / np.float32(2.0)
     return (xyz / (vmax - vmin).max()).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------
+# "next" row N3: the output tree of demo.py (output/<name>/{models,others,geo})
+# ------------------------------------------------------------------------------------------
+def savemeshtes2(pointnp_px3, tcoords_px2, facenp_fx3, facetex_fx3, fname):
+    """models/get3d/get3d_utils/utils_3d.py:27-64: Wavefront OBJ (`v`, `vt`, `f v/vt`) plus the
+    fixed `model_normalized.mtl` next to it; same text, written in one go."""
+    fol, na = os.path.split(fname)
+    na, _ = os.path.splitext(na)
+    with open(os.path.join(fol, "model_normalized.mtl"), "w") as fid:
+        fid.write("newmtl material_0\nKd 1 1 1\nKa 0 0 0\nKs 0.4 0.4 0.4\nNs 10\nillum 2\n"
+                  "map_Kd %s.png\n" % na)
+    f1 = np.asarray(facenp_fx3) + 1
+    f2 = np.asarray(facetex_fx3) + 1
+    parts = ["mtllib %s.mtl\n" % na]
+    parts += ["v %f %f %f\n" % (p[0], p[1], p[2]) for p in np.asarray(pointnp_px3)]
+    parts += ["vt %f %f\n" % (p[0], p[1]) for p in np.asarray(tcoords_px2)]
+    parts.append("usemtl material_0\n")
+    parts += ["f %d/%d %d/%d %d/%d\n" % (a[0], b[0], a[1], b[1], a[2], b[2])
+              for a, b in zip(f1, f2)]
+    with open(fname, "w") as fid:
+        fid.write("".join(parts))
+
+
+def save_textured_mesh(vertices, uvs, faces, mesh_tex_idx, atlas_img, mask, output_root_path):
+    """demo.py:264-307: models/model_normalized.{obj,mtl,png} and others/atlas_wo_background.png.
+    atlas_img [R,R,3] f32 cuda, mask [1,R,R,1] bool.  The 8-bit quantisation + flip runs on the
+    device (pdr_atlas_to_u8); only the uint8 images cross PCIe."""
+    import torch
+    from PIL import Image
+
+    from . import _lib
+    os.makedirs(os.path.join(output_root_path, "models"), exist_ok=True)
+    os.makedirs(os.path.join(output_root_path, "others"), exist_ok=True)
+    savemeshtes2(vertices.detach().cpu().numpy(), uvs.detach().cpu().numpy(),
+                 faces.detach().cpu().numpy(), mesh_tex_idx.detach().cpu().numpy(),
+                 os.path.join(output_root_path, "models", "model_normalized.obj"))
+    R = atlas_img.shape[0]
+    dev = atlas_img.device
+    rgb = torch.empty(R, R, 3, dtype=torch.uint8, device=dev)
+    rgba = torch.empty(R, R, 4, dtype=torch.uint8, device=dev)
+    m = mask[0, :, :, 0].to(torch.uint8).contiguous()
+    _lib.call("pdr_atlas_to_u8", atlas_img.float().contiguous(), m, R, rgb, rgba)
+    Image.fromarray(rgb.cpu().numpy(), "RGB").save(
+        os.path.join(output_root_path, "models", "model_normalized.png"))
+    Image.fromarray(rgba.cpu().numpy(), "RGBA").save(
+        os.path.join(output_root_path, "others", "atlas_wo_background.png"))
+
+
+def loadobjtex(meshfile):
+    """models/get3d/get3d_utils/utils_3d.py:94-140: `v`, `vt`, `f v/vt[/vn]` (triangles; quads are
+    split like the reference).  Returns (vertices f32 [P,3], uvs f32 [T,2] or None,
+    faces int64 [F,3], face_uv_idx int64 [F,3] or None)."""
+    v, vt, f, ft = [], [], [], []
+    with open(meshfile, "r") as fp:
+        for line in fp:
+            d = line.split()
+            if not d:
+                continue
+            if d[0] == "v" and len(d) >= 4:
+                v.append([float(x) for x in d[1:4]])
+            elif d[0] == "vt" and len(d) >= 3:
+                vt.append([float(x) for x in d[1:3]])
+            elif d[0] == "f" and len(d) in (4, 5):
+                c = [x.split("/") for x in d[1:]]
+                tris = [(0, 1, 2)] if len(c) == 3 else [(0, 1, 2), (0, 2, 3)]
+                for t in tris:
+                    f.append([int(c[i][0]) for i in t])
+                    if all(len(c[i]) > 1 and c[i][1] != "" for i in t):
+                        ft.append([int(c[i][1]) for i in t])
+    vertices = np.array(v, dtype=np.float32)
+    faces = np.array(f, dtype=np.int64) - 1
+    has_uv = len(vt) > 0 and len(ft) == len(f)
+    uvs = np.array(vt, dtype=np.float32) if has_uv else None
+    face_uv = (np.array(ft, dtype=np.int64) - 1) if has_uv else None
+    return vertices, uvs, faces, face_uv
+
+
+def save_colored_pc_ply(xyz, rgb, path):
+    """utils/other_utils.py save_colored_pc_ply: binary little-endian PLY, x y z float32 +
+    red green blue uchar (rgb given in [0,1])."""
+    xyz = np.asarray(xyz, dtype=np.float32)
+    rgb8 = (np.asarray(rgb) * 255).astype(np.uint8)
+    rec = np.empty(len(xyz), dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"),
+                                    ("green", "u1"), ("blue", "u1")])
+    rec["x"], rec["y"], rec["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    rec["red"], rec["green"], rec["blue"] = rgb8[:, 0], rgb8[:, 1], rgb8[:, 2]
+    with open(path, "wb") as fh:
+        fh.write(("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\n"
+                  "property float y\nproperty float z\nproperty uchar red\nproperty uchar green\n"
+                  "property uchar blue\nend_header\n" % len(xyz)).encode("ascii"))
+        fh.write(rec.tobytes())
