@@ -24,11 +24,15 @@ F_UNET = 2.2397e12  # FLOPs of one U-Net forward at 256^2, batch 1
 WORKLOAD = "30k-pt synthetic cloud, view_num=8, DDNM_inpaint 256^2 (T_sampling=100), atlas 1024^2"
 
 
-def path_config():
+def path_config(flow="path"):
     from pointdreamer_b200 import demo
-    # configs/default.yaml with the two post-path "next" rows disabled
-    return dict(demo.DEFAULT_CONFIG, view_num=V, res=RES, cam_res=CAM_RES,
-                xatlas_texture_res=ATLAS_RES, complete_unseen_by="unproject", optimize_from=None)
+    # "path": configs/default.yaml with the two post-path "next" rows disabled (SURVEY §8d config 3,
+    # the north-star metric); "default": configs/default.yaml as shipped (complete_unseen_by:
+    # neighbor + optimize_from: ours run after the path)
+    cfg = dict(demo.DEFAULT_CONFIG, view_num=V, res=RES, cam_res=CAM_RES, xatlas_texture_res=ATLAS_RES)
+    if flow == "path":
+        cfg.update(complete_unseen_by="unproject", optimize_from=None)
+    return cfg
 
 
 class ClockSampler:
@@ -181,6 +185,9 @@ def main():
     ap.add_argument("--shapes-per-gpu", type=int, default=1,
                     help="shapes per step per GPU (default 1 = BASELINE configs[1]; 8 with --gpus 8 "
                          "= configs[3], all chains of a GPU in one U-Net batch)")
+    ap.add_argument("--flow", default="path", choices=["path", "default"],
+                    help="path = project->inpaint->unproject (the metric); default = configs/"
+                         "default.yaml as shipped, i.e. + neighbour completion + optimize_color")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -205,7 +212,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
-    cfg = path_config()
+    cfg = path_config(args.flow)
     # ---- setup (untimed): inputs in pinned host memory, weights, cameras ----
     S = args.shapes_per_gpu
     scene_np = synthetic.make_scene(N_POINTS, seed=rank * S, atlas_res=ATLAS_RES)
@@ -294,6 +301,18 @@ def main():
     e2e_ms = max_over_ranks((time.time() - t0) * 1e3) / args.steps
     e2e_value = world * 1000.0 / e2e_ms if S == 1 else None  # the host-buffer leg runs one shape
 
+    # ---- per-stage breakdown of one more (untimed) step: CUDA events at the stage boundaries ----
+    stage_ms = None
+    if S == 1:
+        evs = []
+        inpainter.chains_done = 0
+        demo.colorize_one_mesh(scene_dev["xyz"], scene_dev["rgb"], scene_dev["vertices"],
+                               scene_dev["faces"], scene_dev["f_normals"], xa_dev, cam_info,
+                               device=dev, save_img_path=None, inpainter=inpainter, glctx=None,
+                               logger=None, stage_events=evs, **keys)
+        torch.cuda.synchronize()
+        stage_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(evs[:-1], evs[1:])}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,16 +356,17 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "shapes_per_step_per_gpu": 1,
+        "config": {"workload": WORKLOAD, "shapes_per_step_per_gpu": S, "flow": args.flow,
                    "weights": "random-init ADM 256x256 architecture (552.8M params)",
                    "point_validation_by_o3d": cfg["point_validation_by_o3d"],
-                   "complete_unseen_by": "unproject",
-                   "optimize_from": None, "edge_dilate_kernels": cfg["edge_dilate_kernels"],
+                   "complete_unseen_by": cfg["complete_unseen_by"],
+                   "optimize_from": cfg["optimize_from"], "edge_dilate_kernels": cfg["edge_dilate_kernels"],
                    "l2": "working set (1.9 GB U-Net arena per step) is far larger than the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "shapes/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
+        "stage_ms": stage_ms,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }

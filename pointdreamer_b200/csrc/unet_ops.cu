@@ -537,7 +537,8 @@ __device__ __forceinline__ uint4 pack_8(const float (&y)[8]) {
 }
 
 template <int RESAMPLE>
-__global__ void gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
+__global__ void __launch_bounds__(512, 2)  // <= 64 registers: 4 resident 256-thread CTAs per SM
+gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
   const int C = a.C1 + a.C2;
   const int chunks = C / 8;
   const int chunk = threadIdx.x % chunks, plane = threadIdx.x / chunks;

@@ -54,8 +54,18 @@ def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, c
                       hidden_point_removal_radius, texture_gen_method, point_size, edge_point_size,
                       crop_img, crop_padding, mask_ratio_thresh, optimize_from, edge_dilate_kernels,
                       complete_unseen_by, inpainter, glctx, logger, xatlas_texture_res,
-                      neighbor_fill=None, optimize_color=None, **kwargs):
-    """demo.py:38-253.  Returns (vertices, uvs, faces, mesh_tex_idx, atlas_img[R,R,3], mask)."""
+                      neighbor_fill=None, optimize_color=None, stage_events=None, **kwargs):
+    """demo.py:38-253.  Returns (vertices, uvs, faces, mesh_tex_idx, atlas_img[R,R,3], mask).
+    stage_events: optional list; (name, torch.cuda.Event) pairs are appended at the stage
+    boundaries (bench.py's per-stage breakdown; no synchronisation is added)."""
+
+    def _mark(name):
+        if stage_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            stage_events.append((name, ev))
+
+    _mark("start")
     base_dirs = camera_info['base_dirs']
     cams = camera_info['cams']
     eye_positions = camera_info['eye_positions']
@@ -86,6 +96,7 @@ def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, c
             point_pixels, colors, point_validation, hard_masks, save_img_path, view_num, res,
             point_size, edge_point_size, mask_ratio_thresh)
 
+        _mark("project")
         # ---- INPAINT (demo.py:137-157), including the PNG cache of a previous run
         inpainted_images = None
         if save_img_path is not None:
@@ -98,6 +109,7 @@ def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, c
                 sparse_imgs, hard_mask0s, hard_mask2s, save_img_path, inpainter, view_num,
                 method=texture_gen_method)
 
+        _mark("inpaint")
         # ---- UNPROJECT (demo.py:168-177)
         complete_unseen_by_projection = (complete_unseen_by == 'unproject')
         (atlas_img, shrinked_vis, point_view_ids, points_atlas_pixel_coord, points,
@@ -107,6 +119,7 @@ def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, c
             mesh_normalized_depths, edge_dilate_kernels, save_img_path,
             complete_unseen_by_projection)
 
+        _mark("unproject")
         # ---- after the path (demo.py:180-246): "next" rows
         if complete_unseen_by == 'unproject':
             atlas_img = _un.dilate_atlas(atlas_img, mask)
@@ -119,6 +132,7 @@ def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, c
                                       atlas_img, atlas_painted_mask, use_atlas=True)
         elif complete_unseen_by == 'optimize':
             raise NotImplementedError("complete_unseen_by='optimize' (TextureField) is out of scope")
+        _mark("complete_unseen")
         # ---- demo.py:211-233: refine the atlas against the inpainted views ("next" row N1)
         if optimize_from is not None and optimize_from != 'None':
             if optimize_color is not None:  # caller-supplied replacement
@@ -139,6 +153,7 @@ def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, c
                     padding, inpaint_scale_factors, glctx,
                     shrinked_per_view_per_pixel_visibility=vis, return_images=False)
                 atlas_img = atlas_opt[0].flip(1).permute(1, 2, 0)  # [R,R,3]
+        _mark("optimize_color")
     return vertices, uvs, faces, mesh_tex_idx, atlas_img, mask
 
 
