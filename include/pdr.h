@@ -45,6 +45,16 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
                 const void* residual, void* out, int B, int H, int W, int C1, int C2, int Cout,
                 int taps, int bn, void* stream);
 
+/* ResBlock tail in one GEMM: out = conv3x3(x) + conv1x1(cat(s1,s2)) + bias, i.e. out_layers.3 and
+ * skip_connection of a channel-changing ResBlock (unet.py:206-222, 256) accumulated together
+ * (one fp16 rounding of the sum; the reference rounds each branch and the sum).
+ *   x [B,H,W,C] fp16 ; s1 [B,H,W,S1], s2 [B,H,W,S2] or NULL fp16 ;
+ *   w [Cout][9*C + S1 + S2] fp16 (3x3 weights tap-major, then the 1x1 weights) ;
+ *   bias [Cout] fp32 (sum of both biases) ; out [B,H,W,Cout] fp16 ; bn as in pdr_conv_tc */
+int pdr_conv_tc_skip(const void* x, const void* w, const float* bias, const void* s1,
+                     const void* s2, void* out, int B, int H, int W, int C, int S1, int S2,
+                     int Cout, int bn, void* stream);
+
 /* Individual non-GEMM U-Net kernels (exported for unit parity tests; the engine below calls the
  * same launchers).  NHWC fp16 activations, fp32 parameters.
  *   pdr_linear: out[b][n] = bias[n] + sum_k f(in[b][k]) W[n][k]; mode_in 0 id, 1 SiLU,

@@ -32,6 +32,24 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
                         (const __half*)residual, (__half*)out, nullptr, (cudaStream_t)stream);
 }
 
+int pdr_conv_tc_skip(const void* x, const void* w, const float* bias, const void* s1,
+                     const void* s2, void* out, int B, int H, int W, int C, int S1, int S2,
+                     int Cout, int bn, void* stream) {
+  PDR_CHECK_ARG(x && w && s1 && out, "pdr_conv_tc_skip: null pointer");
+  PDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout % 64 == 0, "pdr_conv_tc_skip: bad shape");
+  if (bn == 0) bn = conv_tc_pick_bn(B, H, W, Cout);
+  ConvTensorMap ma, ms1, ms2, mw;
+  PDR_TRY(conv_tc_make_act_map(&ma, x, B, H, W, C));
+  PDR_TRY(conv_tc_make_act_map(&ms1, s1, B, H, W, S1));
+  if (S2 > 0) {
+    PDR_CHECK_ARG(s2 != nullptr, "pdr_conv_tc_skip: s2 is null but S2=%d", S2);
+    PDR_TRY(conv_tc_make_act_map(&ms2, s2, B, H, W, S2));
+  }
+  PDR_TRY(conv_tc_make_weight_map(&mw, w, Cout, 9 * C + S1 + S2, bn == 512 ? 128 : bn));
+  return conv_tc_launch(&ma, nullptr, &mw, bn, B, H, W, C, 0, Cout, 9, bias, nullptr, (__half*)out,
+                        nullptr, (cudaStream_t)stream, 0.f, &ms1, S2 > 0 ? &ms2 : nullptr, S1, S2);
+}
+
 int pdr_linear(const float* in, const float* W, const float* bias, int B, int K, int N,
                int mode_in, float* out, void* out_fp16, void* stream) {
   PDR_CHECK_ARG(in && W && (out || out_fp16), "pdr_linear: null pointer");

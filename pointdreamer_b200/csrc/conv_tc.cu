@@ -32,6 +32,8 @@ static constexpr int NUM_THREADS = 256;
 struct ConvArgs {
   int B, H, W;
   int C1, C2;  // channels of the two A sources (C2 may be 0)
+  int S1, S2;  // fused 1x1 skip branch: channels of its (up to two) sources, 0 = none.  Its
+               // weights are K columns taps*(C1+C2) .. taps*(C1+C2)+S1+S2-1 of the weight matrix
   int Cout;
   int taps;  // 9 (3x3, pad 1) or 1 (1x1)
   int bw, bh, bb;
@@ -74,10 +76,29 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint32_t tme
   const bool valid = (b < args.B) && (y < args.H) && (x < args.W);
   const size_t row_off = (((size_t)b * args.H + y) * args.W + x) * (size_t)args.Cout + n0;
   const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+  // the residual of chunk ch+1 is requested before chunk ch is processed, so its memory latency
+  // hides behind one chunk of TMEM reads / conversions / stores instead of stalling every chunk
+  const bool has_res = valid && args.residual != nullptr;
+  uint4 rnext[4];
+  if (has_res) {
+    const uint4* rp = (const uint4*)(args.residual + row_off);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+  }
 #pragma unroll 1
   for (int ch = 0; ch < BN / 32; ++ch) {
     uint32_t v[32];
     float s8[4] = {0.f, 0.f, 0.f, 0.f}, q8[4] = {0.f, 0.f, 0.f, 0.f};
+    uint4 rcur[4];
+    if (has_res) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rcur[j] = rnext[j];
+      if (ch + 1 < BN / 32) {
+        const uint4* rp = (const uint4*)(args.residual + row_off + (ch + 1) * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rnext[j] = __ldg(rp + j);
+      }
+    }
     tmem_ld_32x32(taddr + ch * 32, v);
     tmem_ld_wait();
     if (valid) {
@@ -98,10 +119,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint32_t tme
       }
       if (args.residual) {
         // reference adds two fp16 tensors (unet.py:256, :305): fp32 add, one more rounding
-        const uint4* rp = (const uint4*)(args.residual + row_off + ch * 32);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint4 rv = __ldg(rp + j);
+          const uint4 rv = rcur[j];
           const __half* rh = (const __half*)&rv;
 #pragma unroll
           for (int e = 0; e < 8; ++e)
@@ -177,7 +197,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint32_t tme
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB, const ConvArgs args) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmS1,
+               const __grid_constant__ CUtensorMap tmS2, const ConvArgs args) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-B aligned by the ABI: realign to 1024 B for SWIZZLE_128B
@@ -194,7 +215,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   const int Ctot = args.C1 + args.C2;
   const int kchunks_per_tap = Ctot / BLOCK_K;
-  const int num_k = args.taps * kchunks_per_tap;
+  const int num_k_main = args.taps * kchunks_per_tap;
+  const int num_k = num_k_main + (args.S1 + args.S2) / BLOCK_K;  // + fused 1x1 skip branch
   const int tiles_m = args.tiles_b * args.tiles_y * args.tiles_x;
   const int num_tiles = tiles_m * args.tiles_n;
 
@@ -249,12 +271,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-          const int c = kc * BLOCK_K;
-          if (c < args.C1)
-            tma_load_4d(sa, &tmA1, &full_bar[stage], c, x0 + dx, y0 + dy, b0);
-          else
-            tma_load_4d(sa, &tmA2, &full_bar[stage], c - args.C1, x0 + dx, y0 + dy, b0);
-          tma_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
+          if (k < num_k_main) {
+            const int c = kc * BLOCK_K;
+            if (c < args.C1)
+              tma_load_4d(sa, &tmA1, &full_bar[stage], c, x0 + dx, y0 + dy, b0);
+            else
+              tma_load_4d(sa, &tmA2, &full_bar[stage], c - args.C1, x0 + dx, y0 + dy, b0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
+          } else {  // 1x1 skip branch: centre tap of the block input, its own weight columns
+            const int c = (k - num_k_main) * BLOCK_K;
+            if (c < args.S1)
+              tma_load_4d(sa, &tmS1, &full_bar[stage], c, x0, y0, b0);
+            else
+              tma_load_4d(sa, &tmS2, &full_bar[stage], c - args.S1, x0, y0, b0);
+            tma_load_2d(sb, &tmB, &full_bar[stage], args.taps * Ctot + c, n0);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -347,7 +378,8 @@ struct SmemLayout2 {
 template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmB, const ConvArgs args) {
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmS1,
+                const __grid_constant__ CUtensorMap tmS2, const ConvArgs args) {
   constexpr int BN = 256;
   using L = SmemLayout2<STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -365,7 +397,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
 
   const int Ctot = args.C1 + args.C2;
   const int kchunks_per_tap = Ctot / BLOCK_K;
-  const int num_k = args.taps * kchunks_per_tap;
+  const int num_k_main = args.taps * kchunks_per_tap;
+  const int num_k = num_k_main + (args.S1 + args.S2) / BLOCK_K;  // + fused 1x1 skip branch
   const int tiles_m = args.tiles_b * args.tiles_y * args.tiles_x;  // even (checked on the host)
   const int num_pairs = (tiles_m / 2) * args.tiles_n;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -424,12 +457,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);  // bytes of both CTAs
-          const int c = kc * BLOCK_K;
-          if (c < args.C1)
-            tma2_load_4d(sa, &tmA1, &full_bar[stage], c, x0 + dx, y0 + dy, b0);
-          else
-            tma2_load_4d(sa, &tmA2, &full_bar[stage], c - args.C1, x0 + dx, y0 + dy, b0);
-          tma2_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
+          if (k < num_k_main) {
+            const int c = kc * BLOCK_K;
+            if (c < args.C1)
+              tma2_load_4d(sa, &tmA1, &full_bar[stage], c, x0 + dx, y0 + dy, b0);
+            else
+              tma2_load_4d(sa, &tmA2, &full_bar[stage], c - args.C1, x0 + dx, y0 + dy, b0);
+            tma2_load_2d(sb, &tmB, &full_bar[stage], tap * Ctot + c, n0);
+          } else {  // 1x1 skip branch
+            const int c = (k - num_k_main) * BLOCK_K;
+            if (c < args.S1)
+              tma2_load_4d(sa, &tmS1, &full_bar[stage], c, x0, y0, b0);
+            else
+              tma2_load_4d(sa, &tmS2, &full_bar[stage], c - args.S1, x0, y0, b0);
+            tma2_load_2d(sb, &tmB, &full_bar[stage], args.taps * Ctot + c, n0);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -601,7 +643,8 @@ int conv_tc_pick_bn(int B, int H, int W, int Cout) {
 
 template <int BN, int STAGES>
 static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
-                       const ConvArgs& args, cudaStream_t stream) {
+                       const ConvTensorMap* s1, const ConvTensorMap* s2, const ConvArgs& args,
+                       cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES>;
   constexpr int smem_bytes = L::TOTAL + 1024;  // +1024 for the manual realignment
   static bool configured = false;
@@ -613,7 +656,8 @@ static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const C
   const int tiles = args.tiles_b * args.tiles_y * args.tiles_x * args.tiles_n;
   int grid = tiles < num_sms() ? tiles : num_sms();
   conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem_bytes, stream>>>(
-      *(const CUtensorMap*)a1, *(const CUtensorMap*)(a2 ? a2 : a1), *(const CUtensorMap*)w, args);
+      *(const CUtensorMap*)a1, *(const CUtensorMap*)(a2 ? a2 : a1), *(const CUtensorMap*)w,
+      *(const CUtensorMap*)(s1 ? s1 : a1), *(const CUtensorMap*)(s2 ? s2 : (s1 ? s1 : a1)), args);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;
@@ -621,7 +665,8 @@ static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const C
 
 template <int STAGES>
 static int launch_impl2(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
-                        const ConvArgs& args, cudaStream_t stream) {
+                        const ConvTensorMap* s1, const ConvTensorMap* s2, const ConvArgs& args,
+                        cudaStream_t stream) {
   using L = SmemLayout2<STAGES>;
   constexpr int smem_bytes = L::TOTAL + 1024;
   static bool configured = false;
@@ -633,7 +678,8 @@ static int launch_impl2(const ConvTensorMap* a1, const ConvTensorMap* a2, const 
   const int pairs = (args.tiles_b * args.tiles_y * args.tiles_x / 2) * args.tiles_n;
   int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
   conv_tc2_kernel<STAGES><<<2 * clusters, NUM_THREADS, smem_bytes, stream>>>(
-      *(const CUtensorMap*)a1, *(const CUtensorMap*)(a2 ? a2 : a1), *(const CUtensorMap*)w, args);
+      *(const CUtensorMap*)a1, *(const CUtensorMap*)(a2 ? a2 : a1), *(const CUtensorMap*)w,
+      *(const CUtensorMap*)(s1 ? s1 : a1), *(const CUtensorMap*)(s2 ? s2 : (s1 ? s1 : a1)), args);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;
@@ -644,7 +690,11 @@ static int launch_impl2(const ConvTensorMap* a1, const ConvTensorMap* a2, const 
 int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
                    int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
-                   cudaStream_t stream, float qk_scale) {
+                   cudaStream_t stream, float qk_scale, const ConvTensorMap* s1,
+                   const ConvTensorMap* s2, int S1, int S2) {
+  PDR_CHECK_ARG(S1 >= 0 && S2 >= 0 && S1 % BLOCK_K == 0 && S2 % BLOCK_K == 0 &&
+                    (S1 == 0 || s1 != nullptr) && (S2 == 0 || (s2 != nullptr && S1 > 0)),
+                "fused skip branch: channels must be multiples of 64 with their tensor maps");
   PDR_CHECK_ARG(taps == 9 || taps == 1, "taps must be 9 or 1 (got %d)", taps);
   PDR_CHECK_ARG(C1 > 0 && C1 % BLOCK_K == 0 && C2 % BLOCK_K == 0, "C1/C2 must be multiples of 64");
   PDR_CHECK_ARG(BN == 64 || BN == 128 || BN == 256 || BN == 512, "BN must be 64, 128, 256 or 512");
@@ -658,6 +708,8 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   args.W = W;
   args.C1 = C1;
   args.C2 = C2;
+  args.S1 = S1;
+  args.S2 = S2;
   args.Cout = Cout;
   args.taps = taps;
   conv_tc_pick_box(B, H, W, &args.bw, &args.bh, &args.bb);
@@ -679,11 +731,11 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   if (two_cta) {
     PDR_CHECK_ARG((args.tiles_b * args.tiles_y * args.tiles_x) % 2 == 0,
                   "2-CTA conv needs an even number of 128-pixel tiles");
-    return launch_impl2<6>(a1, a2, w, args, stream);
+    return launch_impl2<6>(a1, a2, w, s1, s2, args, stream);
   }
-  if (BN == 256) return launch_impl<256, 4>(a1, a2, w, args, stream);
-  if (BN == 128) return launch_impl<128, 6>(a1, a2, w, args, stream);
-  return launch_impl<64, 8>(a1, a2, w, args, stream);
+  if (BN == 256) return launch_impl<256, 4>(a1, a2, w, s1, s2, args, stream);
+  if (BN == 128) return launch_impl<128, 6>(a1, a2, w, s1, s2, args, stream);
+  return launch_impl<64, 8>(a1, a2, w, s1, s2, args, stream);
 }
 
 }  // namespace pdr

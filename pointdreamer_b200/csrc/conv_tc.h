@@ -23,13 +23,18 @@ int conv_tc_make_act_map(ConvTensorMap* out, const void* ptr, int B, int H, int 
 int conv_tc_make_weight_map(ConvTensorMap* out, const void* ptr, int Cout, int K, int BN);
 
 // out[B,H,W,Cout] = conv(cat(A1,A2)) + bias (+ residual); taps = 9 (3x3 pad 1) or 1 (1x1).
+// Fused 1x1 skip branch (ResBlock skip_connection, unet.py:219-222,256): with S1 (+S2) > 0 the
+// GEMM's K dimension is extended by the channels of cat(s1, s2) read at the centre tap, so
+// out = conv3x3(cat(A1,A2)) + conv1x1(cat(s1,s2)) + bias in ONE accumulation; the weight matrix
+// is [Cout][taps*(C1+C2) + S1+S2] (skip weights appended along K) and bias = both biases summed.
 // qk_scale != 0 (qkv projections only): the q and k channels of the legacy head-major layout
 // (c % 192 < 128) are stored as fp16(fp16(acc + bias) * qk_scale), i.e. the attention's
 // `q * scale`, `k * scale` (unet.py:349-351) is applied here
 int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
                    int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
-                   cudaStream_t stream, float qk_scale = 0.f);
+                   cudaStream_t stream, float qk_scale = 0.f, const ConvTensorMap* s1 = nullptr,
+                   const ConvTensorMap* s2 = nullptr, int S1 = 0, int S2 = 0);
 // number of (m-tile, epilogue-warp) partial rows written per image when stats_partial is used,
 // or 0 when the fused statistics are not available for this spatial size
 int conv_tc_stats_rows_per_image(int H, int W);

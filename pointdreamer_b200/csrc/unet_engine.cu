@@ -85,7 +85,7 @@ class Planner {
 };
 
 struct ConvOp {
-  ConvTensorMap a1, a2, w;
+  ConvTensorMap a1, a2, w, s1, s2;
 };
 
 class UnetEngine {
@@ -260,7 +260,8 @@ class UnetEngine {
 
   // want_sums: also produce the GroupNorm sums of `out` in the epilogue (when the tile allows)
   int add_conv(const Act& x1, const Act* x2, const std::string& pname, int taps, const Act* res,
-               Act& out, bool want_sums = false, float qk_scale = 0.f) {
+               Act& out, bool want_sums = false, float qk_scale = 0.f, const Act* skip1 = nullptr,
+               const Act* skip2 = nullptr) {
     const int stat_rows = want_sums && out.C % 256 == 0 ? conv_tc_stats_rows_per_image(out.H, out.W) : 0;
     if (stat_rows > 0) {
       out.has_sums = true;
@@ -269,7 +270,8 @@ class UnetEngine {
       if (need > partial_bytes_) partial_bytes_ = need;
     }
     const int Cin = x1.C + (x2 ? x2->C : 0);
-    const Param* w = find(pname + ".weight", (size_t)out.C * taps * Cin * 2);
+    const int Cs1 = skip1 ? skip1->C : 0, Cs2 = skip2 ? skip2->C : 0;  // fused 1x1 skip branch
+    const Param* w = find(pname + ".weight", (size_t)out.C * (taps * Cin + Cs1 + Cs2) * 2);
     const Param* b = find(pname + ".bias", (size_t)out.C * 4);
     if (!w || !b) return -1;
     if (out.C % 64 != 0 || x1.C % 64 != 0 || (x2 && x2->C % 64 != 0)) {
@@ -283,7 +285,13 @@ class UnetEngine {
     const int bn = conv_tc_pick_bn(B_, out.H, out.W, out.C);
     PDR_TRY(conv_tc_make_act_map(&c->a1, P<__half>(x1.off), B_, x1.H, x1.W, x1.C));
     if (x2) PDR_TRY(conv_tc_make_act_map(&c->a2, P<__half>(x2->off), B_, x2->H, x2->W, x2->C));
-    PDR_TRY(conv_tc_make_weight_map(&c->w, w->ptr, out.C, taps * Cin, bn == 512 ? 128 : bn));
+    PDR_TRY(conv_tc_make_weight_map(&c->w, w->ptr, out.C, taps * Cin + Cs1 + Cs2,
+                                    bn == 512 ? 128 : bn));
+    if (skip1)
+      PDR_TRY(conv_tc_make_act_map(&c->s1, P<__half>(skip1->off), B_, skip1->H, skip1->W, Cs1));
+    if (skip2)
+      PDR_TRY(conv_tc_make_act_map(&c->s2, P<__half>(skip2->off), B_, skip2->H, skip2->W, Cs2));
+    const bool hs1 = skip1 != nullptr, hs2 = skip2 != nullptr;
     const int H = out.H, W = out.W, C1 = x1.C, C2 = x2 ? x2->C : 0, Co = out.C, Bn = B_;
     const float* bias = (const float*)b->ptr;
     const __half* r = res ? P<__half>(res->off) : nullptr;
@@ -291,10 +299,11 @@ class UnetEngine {
     const bool has2 = x2 != nullptr;
     float* partial = stat_rows > 0 ? P<float>(off_partial_) : nullptr;
     ops.cur_cls = PDR_OP_CONV_TC;
-    ops.cur_flops = 2.0 * Bn * H * W * (double)Co * taps * (C1 + C2);
+    ops.cur_flops = 2.0 * Bn * H * W * (double)Co * (taps * (C1 + C2) + Cs1 + Cs2);
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return conv_tc_launch(&c->a1, has2 ? &c->a2 : nullptr, &c->w, bn, Bn, H, W, C1, C2, Co, taps,
-                            bias, r, o, partial, s, qk_scale);
+                            bias, r, o, partial, s, qk_scale, hs1 ? &c->s1 : nullptr,
+                            hs2 ? &c->s2 : nullptr, Cs1, Cs2);
     });
     if (stat_rows > 0) {
       double* sums = P<double>(out.sums_off);
@@ -345,22 +354,18 @@ class UnetEngine {
     Act a2 = new_act(Ho, Wo, Cout);
     PDR_TRY(add_gn_apply(h1, nullptr, p + ".out_layers.0", 1, true, film_off, true, 0, a2));
     drop(h1);
-    Act skip;
-    bool skip_alloc = false;
-    if (Cin != Cout) {
-      skip = new_act(Ho, Wo, Cout);
-      skip_alloc = true;
-      if (have_xr)
-        PDR_TRY(add_conv(xr, nullptr, p + ".skip_connection", 1, nullptr, skip));
-      else
-        PDR_TRY(add_conv(x1, x2, p + ".skip_connection", 1, nullptr, skip));
-    } else {
-      skip = have_xr ? xr : x1;
-    }
     Act out = new_act(Ho, Wo, Cout);
-    PDR_TRY(add_conv(a2, nullptr, p + ".out_layers.3", 9, &skip, out, true));
+    if (Cin != Cout) {
+      // channel-changing block: skip_connection (1x1) rides in the K loop of out_layers.3 -
+      // "<p>.out_layers.3_skip" = [w3x3 | w1x1] along K, biases summed (set by the host side)
+      const Act& sx = have_xr ? xr : x1;
+      PDR_TRY(add_conv(a2, nullptr, p + ".out_layers.3_skip", 9, nullptr, out, true, 0.f, &sx,
+                       have_xr ? nullptr : x2));
+    } else {
+      Act skip = have_xr ? xr : x1;
+      PDR_TRY(add_conv(a2, nullptr, p + ".out_layers.3", 9, &skip, out, true));
+    }
     drop(a2);
-    if (skip_alloc) drop(skip);
     if (have_xr) drop(xr);
     *result = out;
     return 0;

@@ -143,6 +143,16 @@ class UNetEngine:
         for n in res_names:
             emb_w.append(sd[n + ".emb_layers.1.weight"].detach().to(dev).float())
             emb_b.append(sd[n + ".emb_layers.1.bias"].detach().to(dev).float())
+        # channel-changing ResBlocks: skip_connection (1x1) is accumulated inside out_layers.3's
+        # GEMM -> weights concatenated along K, biases summed in fp32 (unet.py:219-222, 256)
+        for n in res_names:
+            if n + ".skip_connection.weight" in self._tensors:
+                w3 = self._tensors[n + ".out_layers.3.weight"]
+                ws = self._tensors[n + ".skip_connection.weight"]
+                self._set(n + ".out_layers.3_skip.weight", torch.cat([w3, ws], 1))
+                self._set(n + ".out_layers.3_skip.bias",
+                          self._tensors[n + ".out_layers.3.bias"] +
+                          self._tensors[n + ".skip_connection.bias"])
         # stem on the tensor cores: [C][27] -> zero-padded [C][64] (K index = (ky*3+kx)*3 + c)
         stem = self._tensors["input_blocks.0.0.weight"]
         if stem.shape[0] % 64 == 0:

@@ -85,3 +85,37 @@ def test_conv_two_cta(cuda, shape):
     B, H, W, C1, C2, Cout, taps = shape
     err, scale = _run(cuda, B, H, W, C1, C2, Cout, taps, 512, residual=True)
     assert err <= 4e-3 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("shape", [
+    # B, H, W, C, S1, S2, Cout, bn
+    (2, 16, 16, 128, 64, 0, 128, 128),     # one skip source
+    (2, 16, 16, 256, 128, 64, 256, 256),   # concatenated skip input (up path), 1-CTA
+    (1, 8, 8, 128, 192, 64, 128, 64),      # bb = 2, BN = 64
+    (2, 32, 32, 256, 256, 256, 256, 512),  # 2-CTA kernel
+    (4, 64, 64, 64, 64, 64, 256, 0),       # auto tile, many tiles (ring wrap)
+])
+def test_conv_fused_skip(cuda, shape):
+    """out_layers.3 + skip_connection in one GEMM (pdr_conv_tc_skip) vs fp32 torch convs."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    B, H, W, C, S1, S2, Cout, bn = shape
+    g = torch.Generator(device="cpu").manual_seed(1)
+    x = torch.randn(B, H, W, C, generator=g).half().to(cuda)
+    s1 = torch.randn(B, H, W, S1, generator=g).half().to(cuda)
+    s2 = torch.randn(B, H, W, S2, generator=g).half().to(cuda) if S2 else None
+    w3 = (torch.randn(Cout, C, 3, 3, generator=g) / (9 * C) ** 0.5).half().to(cuda)
+    ws = (torch.randn(Cout, S1 + S2, 1, 1, generator=g) / (S1 + S2) ** 0.5).half().to(cuda)
+    b = torch.randn(Cout, generator=g).to(cuda)
+    wk = torch.cat([w3.permute(0, 2, 3, 1).reshape(Cout, 9 * C), ws.reshape(Cout, S1 + S2)], 1).contiguous()
+    out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=cuda)
+    _lib.call("pdr_conv_tc_skip", x, wk, b, s1, s2, out, B, H, W, C, S1, S2, Cout, bn)
+    torch.cuda.synchronize()
+    sin = s1 if s2 is None else torch.cat([s1, s2], -1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w3.float(), b, padding=1) + \
+        F.conv2d(sin.float().permute(0, 3, 1, 2), ws.float())
+    ref = ref.permute(0, 2, 3, 1)
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"fused skip B{B} {H}x{W} C{C}+skip{S1}+{S2}->{Cout} bn{bn}: max_abs_err={err:.3e} ref_max={scale:.3f}")
+    assert err <= 4e-3 * max(scale, 1.0)
