@@ -97,6 +97,9 @@ typedef struct PdrUnetConfig {
  *   GroupNorm / Linear / out.2 parameters fp32 in PyTorch layout;
  *   "emb_all.weight" [sum 2*Cout, 4*mc] / "emb_all.bias": every ResBlock's emb_layers.1
  *   concatenated in module order (input_blocks, middle_block, output_blocks);
+ *   "<resblock>.out_layers.3_skip.weight" fp16 [Cout][9*Cout + Cin] / ".bias" fp32 for every
+ *   ResBlock with a skip_connection: out_layers.3's [Cout][9*Cout] followed along K by the 1x1
+ *   skip weights [Cout][Cin], biases summed - the skip branch runs inside out_layers.3's GEMM;
  *   optional "input_blocks.0.0_tc.weight" fp16 [C][64] (the stem's [C][27] zero padded) +
  *   "input_blocks.0.0_tc.bias": runs the stem as a tensor-core GEMM over 3x3 patches. */
 int pdr_unet_create(const PdrUnetConfig* cfg, void** handle);

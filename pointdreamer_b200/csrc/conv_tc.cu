@@ -620,23 +620,34 @@ int conv_tc_stats_rows_per_image(int H, int W) {
 }
 
 int conv_tc_pick_bn(int B, int H, int W, int Cout) {
-  // Returns the N tile: 512 = the 2-CTA kernel (256-wide tile per SM pair), else the largest
-  // 1-CTA tile that divides Cout, stepping down while SMs would sit idle.
+  // Returns the N tile with the lowest modelled time: 64 / 128 / 256 (1-CTA) or 512 = the 2-CTA
+  // kernel (256-wide tile per SM pair).  Model, fitted to the measured layer table
+  // (profiles/README.md): a k-step of a 128 x bn tile costs max(MMA time, TMA time) with
+  // MMA = bn * 1.078 ns (15.2 TFLOP/s per SM) and TMA = (128 + bn) * 128 B at ~150 GB/s per SM
+  // (the shared-memory fill rate a single CTA sustains from L2: bn = 64 / 128 / 256 reach
+  // 43 / 65 / 80 % of the tensor peak); the SM pair of the 2-CTA kernel stages half of the
+  // weight tile each and is MMA-bound (0.28 us per k-step of a 256 x 256 tile).  Time =
+  // waves over the 148 SMs (74 pairs) x k-step cost; K is common to all candidates.
   int bw, bh, bb;
   conv_tc_pick_box(B, H, W, &bw, &bh, &bb);
   const long long tiles_m = (long long)cdiv(B, bb) * (H / bh) * (W / bw);
-  // SM pairs sharing the weight tile win once there are >= 4 waves of 256x256 tiles (measured:
-  // 1436 vs 1255 TFLOP/s on the 256->256 3x3 layer at 256^2; smaller layers lose to quantisation)
-  if (Cout % 256 == 0 && tiles_m % 2 == 0 && (tiles_m / 2) * (Cout / 256) >= 4 * (num_sms() / 2))
-    return 512;
+  const int sms = num_sms();
   int best = 0;
+  double best_cost = 1e30;
   for (int bn = 256; bn >= 64; bn >>= 1) {
     if (Cout % bn != 0) continue;
-    best = bn;
-    if (tiles_m * (Cout / bn) >= num_sms()) return bn;
-    // BN=64 halves the tensor-core efficiency of a tile: only worth it when even BN=128
-    // leaves more than half of the SMs idle (the 8x8 feature maps)
-    if (bn == 128 && tiles_m * (Cout / 128) * 2 > num_sms()) return 128;
+    const long long tiles = tiles_m * (Cout / bn);
+    const double mma = bn * 1.078e-3, tma = (128 + bn) * 0.853e-3;
+    const double cost = (double)cdiv(tiles, sms) * (mma > tma ? mma : tma);
+    if (cost < best_cost * 0.98) {  // prefer the larger tile on a tie (less L2 traffic)
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  if (Cout % 256 == 0 && tiles_m % 2 == 0) {
+    const long long pairs = (tiles_m / 2) * (Cout / 256);
+    const double cost = (double)cdiv(pairs, sms / 2) * 0.285;
+    if (cost < best_cost * 0.98) best = 512;
   }
   return best;
 }

@@ -63,6 +63,15 @@ def test_unet_engine_plans_without_gpu(lib):
         torso_conv = len(shp) in (3, 4) and not name.startswith("out.")
         nbytes = n * (2 if (torso_conv and name.endswith(".weight")) else 4)
         assert lib.pdr_unet_set_param(h, name.encode(), ctypes.c_void_p(1024), ctypes.c_size_t(nbytes)) == 0
+    # channel-changing ResBlocks: out_layers.3 and skip_connection as ONE weight matrix along K
+    for name, shp in shapes.items():
+        if name.endswith(".skip_connection.weight"):
+            p = name[:-len(".skip_connection.weight")]
+            cout, cin = shp[0], shp[1]
+            lib.pdr_unet_set_param(h, (p + ".out_layers.3_skip.weight").encode(), ctypes.c_void_p(1024),
+                                   ctypes.c_size_t(cout * (9 * cout + cin) * 2))
+            lib.pdr_unet_set_param(h, (p + ".out_layers.3_skip.bias").encode(), ctypes.c_void_p(1024),
+                                   ctypes.c_size_t(cout * 4))
     lib.pdr_unet_set_param(h, b"emb_all.weight", ctypes.c_void_p(1024), ctypes.c_size_t(emb_rows * 1024 * 4))
     lib.pdr_unet_set_param(h, b"emb_all.bias", ctypes.c_void_p(1024), ctypes.c_size_t(emb_rows * 4))
     rc = lib.pdr_unet_workspace_bytes(h, 8, ctypes.byref(need))

@@ -6,6 +6,10 @@ from pointdreamer_b200 import _lib
 
 dev = torch.device("cuda:0")
 shapes = [  # B,H,W,C1,C2,Cout,taps
+    (8, 64, 64, 256, 0, 512, 9),
+    (8, 64, 64, 1024, 0, 512, 9),
+    (8, 32, 32, 1024, 0, 512, 9),
+    (8, 16, 16, 2048, 0, 1024, 9),
     (8, 256, 256, 256, 0, 256, 9),
     (8, 256, 256, 256, 256, 256, 9),
     (8, 128, 128, 256, 0, 256, 9),
@@ -20,7 +24,9 @@ shapes = [  # B,H,W,C1,C2,Cout,taps
 ]
 res = []
 for (B, H, W, C1, C2, Cout, taps) in shapes:
-    for bn in (256, 512):
+    for bn in (64, 128, 256, 512):
+        if Cout % (256 if bn == 512 else bn):
+            continue
         x1 = torch.randn(B, H, W, C1, device=dev).half()
         x2 = torch.randn(B, H, W, C2, device=dev).half() if C2 else None
         w = (torch.randn(Cout, taps * (C1 + C2), device=dev) * 0.02).half()
