@@ -45,6 +45,11 @@ struct ConvArgs {
   // sum of squares of the fp16 outputs, [tiles_m][4][Cout/8][2] floats (null = off)
   float* stats_partial;
   float qk_scale;  // != 0: channels with c % 192 < 128 are re-rounded after a multiply by it
+  // split-K (1-CTA kernel only): the K loop is cut into `ksplit` equal ranges that run as
+  // separate work items; each writes its raw fp32 accumulators to splitk_ws
+  // [ksplit][tiles_m*128][Cout] and splitk_finish_kernel applies the epilogue.  1 = off.
+  int ksplit;
+  float* splitk_ws;
 };
 
 template <int BN, int STAGES>
@@ -194,6 +199,66 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint32_t tme
   }
 }
 
+// split-K work item: raw fp32 accumulators of this K range -> workspace (row = TMEM lane)
+template <int BN>
+__device__ __forceinline__ void epilogue_partial(const ConvArgs& args, uint32_t tmem_acc, int m_lin,
+                                                 int n_tile, int ks, int q, int lane) {
+  const int tiles_m = args.tiles_b * args.tiles_y * args.tiles_x;
+  const size_t row = ((size_t)ks * tiles_m + m_lin) * BLOCK_M + q * 32 + lane;
+  float* dst = args.splitk_ws + row * args.Cout + n_tile * BN;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+  for (int ch = 0; ch < BN / 32; ++ch) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + ch * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *(uint4*)(dst + ch * 32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+}
+
+// sum of the K ranges (fixed order) + bias (+ residual) -> fp16, the same rounding points as
+// epilogue_tile; thread = 8 consecutive output channels of one tile row
+__global__ void splitk_finish_kernel(const ConvArgs args) {
+  const int tiles_m = args.tiles_b * args.tiles_y * args.tiles_x;
+  const int c8n = args.Cout / 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)tiles_m * BLOCK_M * c8n) return;
+  const int c0 = (int)(i % c8n) * 8;
+  const long long row = i / c8n;
+  const int r = (int)(row % BLOCK_M);
+  int m_tile = (int)(row / BLOCK_M);
+  const int pw = r % args.bw, ph = (r / args.bw) % args.bh, pb = r / (args.bw * args.bh);
+  const int tx = m_tile % args.tiles_x;
+  m_tile /= args.tiles_x;
+  const int ty = m_tile % args.tiles_y;
+  const int tb = m_tile / args.tiles_y;
+  const int x = tx * args.bw + pw, y = ty * args.bh + ph, b = tb * args.bb + pb;
+  if (b >= args.B || y >= args.H || x >= args.W) return;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int ks = 0; ks < args.ksplit; ++ks) {
+    const float* p = args.splitk_ws + ((size_t)ks * tiles_m * BLOCK_M + row) * args.Cout + c0;
+    const float4 a0 = *(const float4*)p, a1 = *(const float4*)(p + 4);
+    acc[0] += a0.x, acc[1] += a0.y, acc[2] += a0.z, acc[3] += a0.w;
+    acc[4] += a1.x, acc[5] += a1.y, acc[6] += a1.z, acc[7] += a1.w;
+  }
+  const size_t off = (((size_t)b * args.H + y) * args.W + x) * (size_t)args.Cout + c0;
+  __align__(16) __half o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    o[j] = __float2half_rn(acc[j] + (args.bias ? args.bias[c0 + j] : 0.f));
+  if (args.residual) {
+    const uint4 rv = __ldg((const uint4*)(args.residual + off));
+    const __half* rh = (const __half*)&rv;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(__half2float(o[j]) + __half2float(rh[j]));
+  }
+  *(uint4*)(args.out + off) = *(const uint4*)o;
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -219,6 +284,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int num_k = num_k_main + (args.S1 + args.S2) / BLOCK_K;  // + fused 1x1 skip branch
   const int tiles_m = args.tiles_b * args.tiles_y * args.tiles_x;
   const int num_tiles = tiles_m * args.tiles_n;
+  const int ksplit = args.ksplit;          // K ranges per tile (1 = the whole K loop)
+  const int k_per = num_k / ksplit;        // exact (checked by the launcher)
+  const int num_work = num_tiles * ksplit;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
@@ -250,7 +318,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int tile = work / ksplit;
+        const int k_begin = (work - tile * ksplit) * k_per, k_end = k_begin + k_per;
         const int n_tile = tile % args.tiles_n;
         int m_tile = tile / args.tiles_n;
         const int tx = m_tile % args.tiles_x;
@@ -259,7 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int tb = m_tile / args.tiles_y;
         const int x0 = tx * args.bw, y0 = ty * args.bh, b0 = tb * args.bb;
         const int n0 = n_tile * BN;
-        for (int k = 0; k < num_k; ++k) {
+        for (int k = k_begin; k < k_end; ++k) {
           const int tap = k / kchunks_per_tap;
           const int kc = k - tap * kchunks_per_tap;
           int dy = 0, dx = 0;
@@ -302,11 +372,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int k = 0; k < num_k; ++k) {
+        for (int k = 0; k < k_per; ++k) {
           mbar_wait(&full_bar[stage], phase);  // TMA bytes landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
@@ -336,11 +406,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int tile = work / ksplit;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(args, tmem_base + (uint32_t)(acc * BN), tile / args.tiles_n,
-                        tile % args.tiles_n, q, lane);
+      if (ksplit > 1)
+        epilogue_partial<BN>(args, tmem_base + (uint32_t)(acc * BN), tile / args.tiles_n,
+                             tile % args.tiles_n, work - tile * ksplit, q, lane);
+      else
+        epilogue_tile<BN>(args, tmem_base + (uint32_t)(acc * BN), tile / args.tiles_n,
+                          tile % args.tiles_n, q, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -652,6 +727,45 @@ int conv_tc_pick_bn(int B, int H, int W, int Cout) {
   return best;
 }
 
+int conv_tc_pick_split(int B, int H, int W, int Cout, int num_k, int* bn) {
+  // Layers with fewer tiles than half the SMs (the 8x8 maps) are bound by how fast ONE CTA can
+  // fill shared memory for its whole K loop; cutting K into ranges spreads that over idle SMs.
+  // Same cost model as conv_tc_pick_bn plus ~4 us for the finishing pass.  Returns ksplit and
+  // may raise *bn (a larger tile re-reads less of the activations).
+  if (*bn == 512) return 1;
+  int bw, bh, bb;
+  conv_tc_pick_box(B, H, W, &bw, &bh, &bb);
+  const long long tiles_m = (long long)cdiv(B, bb) * (H / bh) * (W / bw);
+  const int sms = num_sms();
+  auto kstep = [](int n) {
+    const double mma = n * 1.078e-3, tma = (128 + n) * 0.853e-3;
+    return mma > tma ? mma : tma;
+  };
+  const long long base_tiles = tiles_m * (Cout / *bn);
+  if (base_tiles * 2 > sms) return 1;
+  const double base = (double)cdiv(base_tiles, sms) * num_k * kstep(*bn);
+  double best = base * 0.8;  // must win clearly
+  int best_ks = 1, best_bn = *bn;
+  for (int n = 64; n <= 128; n <<= 1) {
+    if (Cout % n != 0) continue;
+    const long long tiles = tiles_m * (Cout / n);
+    for (int ks = 2; ks <= 4; ++ks) {
+      if (num_k % ks != 0 || num_k / ks < 16 || tiles * ks > sms) continue;
+      const double cost = (double)(num_k / ks) * kstep(n) + 4.0;
+      if (cost < best) best = cost, best_ks = ks, best_bn = n;
+    }
+  }
+  *bn = best_bn;
+  return best_ks;
+}
+
+size_t conv_tc_split_workspace_bytes(int B, int H, int W, int Cout, int ksplit) {
+  int bw, bh, bb;
+  conv_tc_pick_box(B, H, W, &bw, &bh, &bb);
+  const size_t tiles_m = (size_t)cdiv(B, bb) * (H / bh) * (W / bw);
+  return ksplit <= 1 ? 0 : (size_t)ksplit * tiles_m * BLOCK_M * Cout * sizeof(float);
+}
+
 template <int BN, int STAGES>
 static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
                        const ConvTensorMap* s1, const ConvTensorMap* s2, const ConvArgs& args,
@@ -664,12 +778,18 @@ static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const C
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  const int tiles = args.tiles_b * args.tiles_y * args.tiles_x * args.tiles_n;
+  const int tiles = args.tiles_b * args.tiles_y * args.tiles_x * args.tiles_n * args.ksplit;
   int grid = tiles < num_sms() ? tiles : num_sms();
   conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem_bytes, stream>>>(
       *(const CUtensorMap*)a1, *(const CUtensorMap*)(a2 ? a2 : a1), *(const CUtensorMap*)w,
       *(const CUtensorMap*)(s1 ? s1 : a1), *(const CUtensorMap*)(s2 ? s2 : (s1 ? s1 : a1)), args);
   PDR_COUNT_LAUNCH();
+  if (args.ksplit > 1) {
+    const long long n = (long long)args.tiles_b * args.tiles_y * args.tiles_x * BLOCK_M *
+                        (args.Cout / 8);
+    splitk_finish_kernel<<<cdiv(n, 256), 256, 0, stream>>>(args);
+    PDR_COUNT_LAUNCH();
+  }
   PDR_LAUNCH_CHECK();
   return 0;
 }
@@ -702,7 +822,12 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
                    int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
                    cudaStream_t stream, float qk_scale, const ConvTensorMap* s1,
-                   const ConvTensorMap* s2, int S1, int S2) {
+                   const ConvTensorMap* s2, int S1, int S2, int ksplit, float* splitk_ws) {
+  PDR_CHECK_ARG(ksplit >= 1 && (ksplit == 1 || (splitk_ws != nullptr && BN != 512 &&
+                                                stats_partial == nullptr && qk_scale == 0.f)),
+                "split-K needs a workspace, a 1-CTA tile, and no fused statistics / qk scaling");
+  PDR_CHECK_ARG((taps * ((C1 + C2) / BLOCK_K) + (S1 + S2) / BLOCK_K) % ksplit == 0,
+                "split-K: %d does not divide the number of K steps", ksplit);
   PDR_CHECK_ARG(S1 >= 0 && S2 >= 0 && S1 % BLOCK_K == 0 && S2 % BLOCK_K == 0 &&
                     (S1 == 0 || s1 != nullptr) && (S2 == 0 || (s2 != nullptr && S1 > 0)),
                 "fused skip branch: channels must be multiples of 64 with their tensor maps");
@@ -735,6 +860,8 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   args.out = out;
   args.stats_partial = stats_partial;
   args.qk_scale = qk_scale;
+  args.ksplit = ksplit;
+  args.splitk_ws = splitk_ws;
   PDR_CHECK_ARG(qk_scale == 0.f || (Cout % 192 == 0 && !residual && !stats_partial),
                 "qk_scale is for qkv projections (Cout %% 192 == 0, no residual, no statistics)");
   PDR_CHECK_ARG(!stats_partial || (args.bb == 1 && Cout % 32 == 0),

@@ -34,7 +34,13 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
                    int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
                    cudaStream_t stream, float qk_scale = 0.f, const ConvTensorMap* s1 = nullptr,
-                   const ConvTensorMap* s2 = nullptr, int S1 = 0, int S2 = 0);
+                   const ConvTensorMap* s2 = nullptr, int S1 = 0, int S2 = 0, int ksplit = 1,
+                   float* splitk_ws = nullptr);
+// split-K for layers with too few tiles to fill the GPU: returns the number of K ranges (1 = off)
+// for a layer with `num_k` 64-channel K steps and may change *bn; the workspace holds the fp32
+// partial tiles (conv_tc_split_workspace_bytes) and a finishing kernel applies the epilogue
+int conv_tc_pick_split(int B, int H, int W, int Cout, int num_k, int* bn);
+size_t conv_tc_split_workspace_bytes(int B, int H, int W, int Cout, int ksplit);
 // number of (m-tile, epilogue-warp) partial rows written per image when stats_partial is used,
 // or 0 when the fused statistics are not available for this spatial size
 int conv_tc_stats_rows_per_image(int H, int W);

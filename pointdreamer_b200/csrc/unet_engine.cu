@@ -279,10 +279,20 @@ class UnetEngine {
                 x1.C, x2 ? x2->C : 0, out.C);
       return -1;
     }
+    // tile + split-K choice; the split-K partial tiles share the statistics scratch (a conv has
+    // one or the other, and its consumer kernel follows it on the stream)
+    int bn = conv_tc_pick_bn(B_, out.H, out.W, out.C);
+    int ksplit = 1;
+    if (stat_rows == 0 && qk_scale == 0.f && taps == 9) {
+      // decided for a FIXED reference batch of 8: splitting changes the fp32 summation order, and
+      // a chain's bits must not depend on the batch it happens to run in
+      ksplit = conv_tc_pick_split(8, out.H, out.W, out.C, taps * (Cin / 64) + (Cs1 + Cs2) / 64, &bn);
+      const size_t need = conv_tc_split_workspace_bytes(B_, out.H, out.W, out.C, ksplit);
+      if (need > partial_bytes_) partial_bytes_ = need;
+    }
     if (dry_) return 0;
     ConvOp* c = new ConvOp();
     conv_ops.push_back(c);
-    const int bn = conv_tc_pick_bn(B_, out.H, out.W, out.C);
     PDR_TRY(conv_tc_make_act_map(&c->a1, P<__half>(x1.off), B_, x1.H, x1.W, x1.C));
     if (x2) PDR_TRY(conv_tc_make_act_map(&c->a2, P<__half>(x2->off), B_, x2->H, x2->W, x2->C));
     PDR_TRY(conv_tc_make_weight_map(&c->w, w->ptr, out.C, taps * Cin + Cs1 + Cs2,
@@ -298,12 +308,13 @@ class UnetEngine {
     __half* o = P<__half>(out.off);
     const bool has2 = x2 != nullptr;
     float* partial = stat_rows > 0 ? P<float>(off_partial_) : nullptr;
+    float* split_ws = ksplit > 1 ? P<float>(off_partial_) : nullptr;
     ops.cur_cls = PDR_OP_CONV_TC;
     ops.cur_flops = 2.0 * Bn * H * W * (double)Co * (taps * (C1 + C2) + Cs1 + Cs2);
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return conv_tc_launch(&c->a1, has2 ? &c->a2 : nullptr, &c->w, bn, Bn, H, W, C1, C2, Co, taps,
                             bias, r, o, partial, s, qk_scale, hs1 ? &c->s1 : nullptr,
-                            hs2 ? &c->s2 : nullptr, Cs1, Cs2);
+                            hs2 ? &c->s2 : nullptr, Cs1, Cs2, ksplit, split_ws);
     });
     if (stat_rows > 0) {
       double* sums = P<double>(out.sums_off);

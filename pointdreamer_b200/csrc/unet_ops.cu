@@ -736,8 +736,11 @@ int resample_launch(const __half* x, int B, int H, int W, int C, int mode, __hal
 
 // --------------------------------------------------------------- fp32 head ----
 // unet.py:663-664: h.float() -> GroupNorm -> SiLU -> conv3x3(C -> n_out) in fp32, NCHW fp32 out.
-// Block = 8 rows x 32 cols of output pixels, thread = 4 consecutive pixels of a row;
-// channels are streamed through shared memory in chunks of HEAD_CC.
+// Block = 16 rows x 32 cols of output pixels, thread = 4 consecutive pixels of a row;
+// channels are streamed through shared memory in chunks of HEAD_CC.  The staging pass (GroupNorm
+// affine + SiLU of the halo tile) used to cost more instructions than the convolution itself:
+// SiLU uses ex2.approx / rcp.approx (relative error ~1e-6, three orders of magnitude below the
+// fp16 noise of the tensor it is applied to).
 static constexpr int HEAD_CC = 16;
 static constexpr int HEAD_TW = 32, HEAD_TH = 16;
 static constexpr int HEAD_THREADS = 128;  // 16 rows x 8 groups of 4 pixels
@@ -798,7 +801,7 @@ head_kernel(const __half* __restrict__ h, const float* __restrict__ stats,
         const __half* hh = (const __half*)&raw;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          v[j] = silu_f(h2f(hh[j]) * s_ab[c8 * 8 + j] + s_ab[HEAD_CC + c8 * 8 + j]);
+          v[j] = silu_fast(h2f(hh[j]) * s_ab[c8 * 8 + j] + s_ab[HEAD_CC + c8 * 8 + j]);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.f;

@@ -119,3 +119,20 @@ def test_conv_fused_skip(cuda, shape):
     scale = ref.abs().max().item()
     print(f"fused skip B{B} {H}x{W} C{C}+skip{S1}+{S2}->{Cout} bn{bn}: max_abs_err={err:.3e} ref_max={scale:.3f}")
     assert err <= 4e-3 * max(scale, 1.0)
+
+
+def test_unet_engine_split_k_layers_batch_invariant(cuda):
+    """The 8x8 layers run split-K (decided for a fixed reference batch): a chain's output bits are
+    the same at batch 1, 3 and 8 of the full-size model."""
+    from pointdreamer_b200.unet import UNetEngine, random_state_dict, DEFAULT_MODEL_CONFIG
+    sd = random_state_dict(DEFAULT_MODEL_CONFIG, 7, cuda)
+    eng = UNetEngine(sd, DEFAULT_MODEL_CONFIG, device=cuda)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(8, 3, 256, 256, generator=g).to(cuda)
+    t = torch.full((8,), 310.0, device=cuda)
+    y8 = eng(x, t, n_out=3).clone()
+    y3 = eng(x[:3].contiguous(), t[:3].contiguous(), n_out=3).clone()
+    y1 = eng(x[5:6].contiguous(), t[5:6].contiguous(), n_out=3).clone()
+    assert torch.isfinite(y8).all()
+    assert torch.equal(y3, y8[:3])
+    assert torch.equal(y1[0], y8[5])
