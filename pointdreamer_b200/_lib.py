@@ -8,7 +8,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpdr.so")
+# PDR_LIB_PATH: load another build of the same ABI (A/B timing of kernel variants in one run)
+LIB_PATH = os.environ.get("PDR_LIB_PATH") or os.path.join(_HERE, "libpdr.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "pdr.h")
 
 _lib = None
