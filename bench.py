@@ -323,8 +323,10 @@ def main():
     conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
     total_prof_ms = sum(v["ms"] for v in prof.values())
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01f_conv_traffic.json")
-    if os.path.exists(tp):  # DRAM bytes per conv launch from the committed ncu capture
+    import glob
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_traffic.json")))
+    tp = cands[-1] if cands else ""
+    if tp:  # DRAM bytes per conv launch from the newest committed ncu capture
         tj = json.load(open(tp))
         traffic, traffic_src = tj["avg_traffic_bytes_per_launch"], tj["source"]
     roofline = {
