@@ -11,7 +11,6 @@
 // tiles are double buffered in shared memory with the next tile's global loads in flight during
 // the current tile's math; no T x T matrix is ever written to HBM.  q and k arrive either raw
 // (scaled here while staging) or already scaled by the qkv conv's epilogue (PRESCALED).
-#include <stdlib.h>
 #include "common.cuh"
 #include "unet_ops.h"
 
@@ -240,8 +239,7 @@ int attention_launch(const __half* qkv, int B, int T, int heads, int prescaled, 
   PDR_CHECK_ARG(T % 64 == 0 && T >= 64, "attention: sequence length %d must be a multiple of 64", T);
   PDR_CHECK_ARG(heads >= 1 && B >= 1, "attention: bad shape");
   // 128 queries per CTA halves the K/V re-reads; small maps keep 64 so the grid still fills
-  static const bool force4 = getenv("PDR_ATTN_NW4") != nullptr;  // experiment switch
-  if (!force4 && T % 128 == 0 && (T / 128) * heads * B >= 2 * 148)
+  if (T % 128 == 0 && (T / 128) * heads * B >= 2 * 148)
     return attention_launch_nw<8>(qkv, B, T, heads, prescaled, out, stream);
   return attention_launch_nw<4>(qkv, B, T, heads, prescaled, out, stream);
 }
