@@ -101,3 +101,16 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.PdrError):
         _lib.load()
+
+
+def test_texture_psnr_metric():
+    import numpy as np
+    from pointdreamer_b200 import metrics
+    a = np.zeros((8, 8, 3), dtype=np.uint8)
+    b = a.copy()
+    assert metrics.calculate_psnr(a, b) == float("inf")
+    b[...] = 1
+    assert abs(metrics.calculate_psnr(a, b) - 20 * np.log10(255.0)) < 1e-9
+    atlas = np.linspace(-0.1, 1.1, 8 * 8 * 3, dtype=np.float32).reshape(8, 8, 3)
+    q = metrics.atlas_to_uint8(atlas)
+    assert q.dtype == np.uint8 and q[-1, 0, 0] == 0 and q[0, -1, -1] == 255

@@ -65,3 +65,8 @@ def test_default_yaml_flow_matches_oracle(cuda):
           f"texels off by >1e-3: {(err.max(-1) > 1e-3).mean():.2e}")
     assert psnr > 55.0
     assert (err.max(-1) > 1e-3).mean() < 5e-3
+    # the metric of BASELINE.json: texture PSNR on the 8-bit atlas image (psnr_ssmi.py:23-42)
+    from pointdreamer_b200 import metrics
+    p8 = metrics.calculate_psnr(metrics.atlas_to_uint8(atlas), metrics.atlas_to_uint8(ref))
+    print(f"8-bit texture PSNR, CUDA flow vs oracle flow: {p8:.1f} dB")
+    assert p8 > 50.0

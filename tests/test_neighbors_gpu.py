@@ -64,3 +64,23 @@ def test_vertex_colors_when_use_atlas_false(cuda):
         use_atlas=False)
     assert c.shape == (v.shape[0], 3) and f.max().item() < v.shape[0]
     assert torch.isfinite(c).all()
+
+
+def test_nothing_to_inpaint_is_a_plain_fill(cuda):
+    """Every face seen: no subdivision, no colouring round changes anything, the result is the atlas
+    with its vertex texels rewritten by themselves and the gutters nearest-filled."""
+    from pointdreamer_b200 import unproject as un
+    sc, atlas, painted, ids = inputs(unseen_below=-10.0)
+    xa = sc["xatlas_dict"]
+    mask = xa["mask"][0, :, :, 0]
+    rng = np.random.default_rng(0)
+    atlas = rng.random(atlas.shape).astype(np.float32) * mask[..., None]
+    none = np.zeros(0, dtype=np.int64)
+    out = un.paint_invisible_areas_by_neighbors(
+        _t(sc["vertices"], cuda), _t(sc["faces"], cuda), _t(xa["uvs"], cuda),
+        _t(xa["mesh_tex_idx"], cuda), _t(none, cuda), _t(atlas, cuda), _t(mask, cuda),
+        use_atlas=True).cpu().numpy()
+    ref, tie, rounds = onb.paint_invisible_areas_by_neighbors(
+        sc["vertices"], sc["faces"], xa["uvs"], xa["mesh_tex_idx"], none, atlas, mask)
+    assert np.array_equal(out, ref)
+    assert np.array_equal(out[mask], atlas[mask])

@@ -60,3 +60,18 @@ def test_host_subdivide_matches_oracle_on_cpu():
         vo, fo, uvo, fuvo = onb.subdivide_with_uv(vo, fo, fuvo, uvo, face_index=ids)
     assert np.array_equal(f.numpy(), fo) and np.array_equal(fuv.numpy(), fuvo)
     assert np.array_equal(v.numpy(), vo) and np.array_equal(uv.numpy(), uvo)
+
+
+def test_subdivide_with_no_faces_selected_is_identity():
+    import torch
+    from pointdreamer_b200.mesh_utils import subdivide_with_uv
+    sc, atlas, painted, ids = inputs()
+    xa = sc["xatlas_dict"]
+    t = torch.from_numpy
+    none = np.zeros(0, dtype=np.int64)
+    v, f, uv, fuv = subdivide_with_uv(t(sc["vertices"]), t(sc["faces"]), t(xa["mesh_tex_idx"]),
+                                      t(xa["uvs"]), face_index=t(none))
+    assert np.array_equal(v.numpy(), sc["vertices"]) and np.array_equal(f.numpy(), sc["faces"])
+    vo, fo, uvo, fuvo = onb.subdivide_with_uv(sc["vertices"], sc["faces"], xa["mesh_tex_idx"],
+                                              xa["uvs"], face_index=none)
+    assert np.array_equal(fo, sc["faces"]) and np.array_equal(uvo, xa["uvs"])
