@@ -22,14 +22,16 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
   PDR_CHECK_ARG(Cout % 64 == 0, "pdr_conv_tc: Cout (%d) must be a multiple of 64", Cout);
   if (bn == 0) bn = conv_tc_pick_bn(B, H, W, Cout);
   ConvTensorMap ma1, ma2, mw;
-  PDR_TRY(conv_tc_make_act_map(&ma1, x1, B, H, W, C1));
+  const int halo = conv_tc_halo_ok(H, W, taps) ? 1 : 0;
+  PDR_TRY(conv_tc_make_act_map(&ma1, x1, B, H, W, C1, halo));
   if (C2 > 0) {
     PDR_CHECK_ARG(x2 != nullptr, "pdr_conv_tc: x2 is null but C2=%d", C2);
-    PDR_TRY(conv_tc_make_act_map(&ma2, x2, B, H, W, C2));
+    PDR_TRY(conv_tc_make_act_map(&ma2, x2, B, H, W, C2, halo));
   }
   PDR_TRY(conv_tc_make_weight_map(&mw, w, Cout, taps * (C1 + C2), bn == 512 ? 128 : bn));
   return conv_tc_launch(&ma1, C2 > 0 ? &ma2 : nullptr, &mw, bn, B, H, W, C1, C2, Cout, taps, bias,
-                        (const __half*)residual, (__half*)out, nullptr, (cudaStream_t)stream);
+                        (const __half*)residual, (__half*)out, nullptr, (cudaStream_t)stream, 0.f,
+                        nullptr, nullptr, 0, 0, 1, nullptr, halo);
 }
 
 int pdr_conv_tc_skip(const void* x, const void* w, const float* bias, const void* s1,
@@ -39,15 +41,17 @@ int pdr_conv_tc_skip(const void* x, const void* w, const float* bias, const void
   PDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout % 64 == 0, "pdr_conv_tc_skip: bad shape");
   if (bn == 0) bn = conv_tc_pick_bn(B, H, W, Cout);
   ConvTensorMap ma, ms1, ms2, mw;
-  PDR_TRY(conv_tc_make_act_map(&ma, x, B, H, W, C));
-  PDR_TRY(conv_tc_make_act_map(&ms1, s1, B, H, W, S1));
+  const int halo = conv_tc_halo_ok(H, W, 9) ? 1 : 0;
+  PDR_TRY(conv_tc_make_act_map(&ma, x, B, H, W, C, halo));
+  PDR_TRY(conv_tc_make_act_map(&ms1, s1, B, H, W, S1, halo));
   if (S2 > 0) {
     PDR_CHECK_ARG(s2 != nullptr, "pdr_conv_tc_skip: s2 is null but S2=%d", S2);
-    PDR_TRY(conv_tc_make_act_map(&ms2, s2, B, H, W, S2));
+    PDR_TRY(conv_tc_make_act_map(&ms2, s2, B, H, W, S2, halo));
   }
   PDR_TRY(conv_tc_make_weight_map(&mw, w, Cout, 9 * C + S1 + S2, bn == 512 ? 128 : bn));
   return conv_tc_launch(&ma, nullptr, &mw, bn, B, H, W, C, 0, Cout, 9, bias, nullptr, (__half*)out,
-                        nullptr, (cudaStream_t)stream, 0.f, &ms1, S2 > 0 ? &ms2 : nullptr, S1, S2);
+                        nullptr, (cudaStream_t)stream, 0.f, &ms1, S2 > 0 ? &ms2 : nullptr, S1, S2, 1,
+                        nullptr, halo);
 }
 
 int pdr_linear(const float* in, const float* W, const float* bias, int B, int K, int N,

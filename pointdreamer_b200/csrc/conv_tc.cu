@@ -19,6 +19,7 @@
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4..7 = epilogue (TMEM -> registers -> +bias (+residual) -> fp16 -> global).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv_tc.h"
 
@@ -50,6 +51,7 @@ struct ConvArgs {
   // [ksplit][tiles_m*128][Cout] and splitk_finish_kernel applies the epilogue.  1 = off.
   int ksplit;
   float* splitk_ws;
+  int halo;  // 1: conv_halo_kernel (8 x 16 pixel tiles, activation maps encoded with the halo box)
 };
 
 template <int BN, int STAGES>
@@ -330,8 +332,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int x0 = tx * args.bw, y0 = ty * args.bh, b0 = tb * args.bb;
         const int n0 = n_tile * BN;
         for (int k = k_begin; k < k_end; ++k) {
-          const int tap = k / kchunks_per_tap;
-          const int kc = k - tap * kchunks_per_tap;
+          // chunk-major K order (all taps of a 64-channel chunk, then the next chunk): the same
+          // order as the halo kernel, so every variant accumulates a given output identically
+          const int kc = k / args.taps;
+          const int tap = k - kc * args.taps;
           int dy = 0, dx = 0;
           if (args.taps == 9) {
             dy = tap / 3 - 1;
@@ -521,8 +525,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         const int x0 = tx * args.bw, y0 = ty * args.bh, b0 = tb * args.bb;
         const int n0 = n_tile * BN + (int)rank * 128;  // this CTA's half of the weight rows
         for (int k = 0; k < num_k; ++k) {
-          const int tap = k / kchunks_per_tap;
-          const int kc = k - tap * kchunks_per_tap;
+          // chunk-major K order (all taps of a 64-channel chunk, then the next chunk): the same
+          // order as the halo kernel, so every variant accumulates a given output identically
+          const int kc = k / args.taps;
+          const int tap = k - kc * args.taps;
           int dy = 0, dx = 0;
           if (args.taps == 9) {
             dy = tap / 3 - 1;
@@ -620,6 +626,245 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Halo variant for 3x3 convolutions on maps of at least 16 x 8: the A operand of ALL NINE taps of
+// a 64-channel chunk comes from ONE shared-memory tile.  The output tile is 8 pixels wide and 16
+// tall; TMA loads its 10 x 18 halo (zero filled outside the image = the conv padding) as 180 rows
+// of 128 B (SWIZZLE_128B).  An 8-pixel output row is one 8-row core-matrix group, so tap (dy,dx) is
+// the SAME tile seen through a descriptor whose start address is shifted by (dy*10+dx) rows and
+// whose groups are 10 rows (1280 B) apart - the swizzle is a function of the absolute shared
+// memory address, so whole-row shifts keep it consistent (tools/experiments/halo_desc_test.cu).
+// Per k-step a CTA now fills 23 KB / 9 + its weight tile instead of 16 KB + its weight tile:
+// L2 -> shared memory traffic drops by 40 % (2-CTA) to 46 % (1-CTA, BN = 128), which lifts the
+// 1-CTA tiles off the shared-memory fill limit.  Two rings: A (one slot per chunk) and B (one
+// slot per tap).  TWO = cta_group::2 pair (BN = 256, each CTA stages half of the weight tile).
+static constexpr int HALO_W = 10, HALO_H = 18;
+static constexpr int HALO_BYTES = HALO_W * HALO_H * BLOCK_K * 2;            // 23040
+static constexpr int HALO_STAGE = (HALO_BYTES + 1023) / 1024 * 1024;        // 23552
+
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <bool TWO, int BN, int AST, int BST>
+struct SmemLayoutHalo {
+  static constexpr int B_ROWS = TWO ? 128 : BN;  // weight rows staged by this CTA
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
+  static constexpr int B_OFFSET = AST * HALO_STAGE;
+  static constexpr int BAR_OFFSET = B_OFFSET + BST * B_BYTES;
+  // a_full[AST], a_empty[AST], b_full[BST], b_empty[BST], tmem_full[2], tmem_empty[2], tmem ptr
+  static constexpr int TOTAL = BAR_OFFSET + (2 * AST + 2 * BST + 4) * 8 + 16;
+};
+
+template <bool TWO, int BN, int AST, int BST>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmS1,
+                 const __grid_constant__ CUtensorMap tmS2, const ConvArgs args) {
+  using L = SmemLayoutHalo<TWO, BN, AST, BST>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = (uint64_t*)(smem + L::BAR_OFFSET);
+  uint64_t* a_empty = a_full + AST;
+  uint64_t* b_full = a_empty + AST;
+  uint64_t* b_empty = b_full + BST;
+  uint64_t* tmem_full = b_empty + BST;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+
+  const int Ctot = args.C1 + args.C2;
+  const int chunks_main = Ctot / BLOCK_K;
+  const int chunks_all = chunks_main + (args.S1 + args.S2) / BLOCK_K;  // + fused 1x1 skip branch
+  const int tiles_m = args.tiles_b * args.tiles_y * args.tiles_x;
+  // work items: 1-CTA = (m tile, n tile); 2-CTA = (pair of m tiles, n tile) per cluster
+  const int num_work = (TWO ? tiles_m / 2 : tiles_m) * args.tiles_n;
+  const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr uint32_t TXMUL = TWO ? 2u : 1u;  // the leader's barrier counts the bytes of both CTAs
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    if (args.C2 > 0) tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < AST; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < BST; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], TWO ? 8 : 4);  // epilogue warps (of both CTAs in 2-CTA mode)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    if (TWO) {
+      tmem_alloc2(tmem_ptr_smem, 2 * BN);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_ptr_smem, 2 * BN);
+      tmem_relinquish();
+    }
+  }
+  tc_fence_before();
+  if (TWO) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer ====
+    if (elect_one_sync()) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int work = worker; work < num_work; work += num_workers) {
+        const int n_tile = work % args.tiles_n;
+        int m_tile = TWO ? (work / args.tiles_n) * 2 + (int)rank : work / args.tiles_n;
+        const int tx = m_tile % args.tiles_x;
+        m_tile /= args.tiles_x;
+        const int ty = m_tile % args.tiles_y;
+        const int tb = m_tile / args.tiles_y;
+        const int x0 = tx * 8 - 1, y0 = ty * 16 - 1;  // halo origin (may be -1: zero fill)
+        const int n0 = n_tile * BN + (TWO ? (int)rank * 128 : 0);
+        for (int ch = 0; ch < chunks_all; ++ch) {
+          const bool main_chunk = ch < chunks_main;
+          mbar_wait(&a_empty[as], aph ^ 1);
+          uint8_t* sa = smem + as * HALO_STAGE;
+          if (leader) mbar_expect_tx(&a_full[as], TXMUL * HALO_BYTES);
+          int c = (main_chunk ? ch : ch - chunks_main) * BLOCK_K;
+          const CUtensorMap* tm;
+          if (main_chunk) {
+            tm = c < args.C1 ? &tmA1 : &tmA2;
+            if (c >= args.C1) c -= args.C1;
+          } else {
+            tm = c < args.S1 ? &tmS1 : &tmS2;
+            if (c >= args.S1) c -= args.S1;
+          }
+          if (TWO)
+            tma2_load_4d(sa, tm, &a_full[as], c, x0, y0, tb);
+          else
+            tma_load_4d(sa, tm, &a_full[as], c, x0, y0, tb);
+          if (++as == AST) {
+            as = 0;
+            aph ^= 1;
+          }
+          const int ntaps = main_chunk ? 9 : 1;
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            uint8_t* sb = smem + L::B_OFFSET + bs * L::B_BYTES;
+            if (leader) mbar_expect_tx(&b_full[bs], TXMUL * L::B_BYTES);
+            const int kcoord = main_chunk ? t * Ctot + ch * BLOCK_K
+                                          : 9 * Ctot + (ch - chunks_main) * BLOCK_K;
+            if (TWO)
+              tma2_load_2d(sb, &tmB, &b_full[bs], kcoord, n0);
+            else
+              tma_load_2d(sb, &tmB, &b_full[bs], kcoord, n0);
+            if (++bs == BST) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 && leader) {
+    // ======================================================= MMA issuer ====
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_f16(TWO ? 2 * BLOCK_M : BLOCK_M, BN);
+      int as = 0, bs = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, acc_phase = 0;
+      for (int work = worker; work < num_work; work += num_workers) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        uint32_t first = 1;
+        for (int ch = 0; ch < chunks_all; ++ch) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + as * HALO_STAGE);
+          const int ntaps = ch < chunks_main ? 9 : 1;
+          for (int t = 0; t < ntaps; ++t) {
+            const int tap = ntaps == 9 ? t : 4;  // the skip branch reads the centre tap
+            const uint32_t a_tap = sa + (uint32_t)((tap / 3) * HALO_W + tap % 3) * 128u;
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(smem + L::B_OFFSET + bs * L::B_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+              const uint64_t adesc = make_smem_desc_sw128_sbo(a_tap + kk * UMMA_K * 2, HALO_W * 128);
+              const uint64_t bdesc = make_smem_desc_sw128(sb + kk * UMMA_K * 2);
+              if (TWO)
+                umma2_f16(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+              else
+                umma_f16(tmem_d, adesc, bdesc, idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            if (TWO) umma2_commit_multicast(&b_empty[bs]); else umma_commit(&b_empty[bs]);
+            if (++bs == BST) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+          if (TWO) umma2_commit_multicast(&a_empty[as]); else umma_commit(&a_empty[as]);
+          if (++as == AST) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+        if (TWO) umma2_commit_multicast(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ========================================================= epilogue ====
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int work = worker; work < num_work; work += num_workers) {
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int m_lin = TWO ? (work / args.tiles_n) * 2 + (int)rank : work / args.tiles_n;
+      epilogue_tile<BN>(args, tmem_base + (uint32_t)(acc * BN), m_lin, work % args.tiles_n, q, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (TWO) mbar_arrive_cluster(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  if (TWO) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    if (TWO) tmem_dealloc2(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
 // ------------------------------------------------------------------ host ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -651,14 +896,24 @@ void conv_tc_pick_box(int B, int H, int W, int* bw, int* bh, int* bb) {
   (void)B;
 }
 
-int conv_tc_make_act_map(ConvTensorMap* out, const void* ptr, int B, int H, int W, int C) {
+bool conv_tc_halo_ok(int H, int W, int taps) {
+  static const bool disabled = getenv("PDR_NO_HALO") != nullptr;  // A/B switch (profiles/README.md)
+  return !disabled && taps == 9 && W % 8 == 0 && H % 16 == 0;
+}
+
+int conv_tc_make_act_map(ConvTensorMap* out, const void* ptr, int B, int H, int W, int C,
+                         int halo) {
   EncodeTiledFn enc = get_encode_fn();
   PDR_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
   PDR_CHECK_ARG(C % BLOCK_K == 0, "activation channels (%d) must be a multiple of 64", C);
   PDR_CHECK_ARG(((uintptr_t)ptr & 15) == 0, "activation pointer must be 16-byte aligned");
   int bw, bh, bb;
   conv_tc_pick_box(B, H, W, &bw, &bh, &bb);
-  PDR_CHECK_ARG(bw * bh * bb == 128 && W % bw == 0 && H % bh == 0,
+  if (halo) {
+    PDR_CHECK_ARG(W % 8 == 0 && H % 16 == 0, "halo tiles need W %% 8 == 0 and H %% 16 == 0");
+    bw = HALO_W, bh = HALO_H, bb = 1;  // the 10 x 18 halo of an 8 x 16 output tile
+  }
+  PDR_CHECK_ARG(halo || (bw * bh * bb == 128 && W % bw == 0 && H % bh == 0),
                 "unsupported spatial size %dx%d for the 128-pixel tile", H, W);
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
@@ -816,13 +1071,55 @@ static int launch_impl2(const ConvTensorMap* a1, const ConvTensorMap* a2, const 
   return 0;
 }
 
+template <bool TWO, int BN, int AST, int BST>
+static int launch_halo(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
+                       const ConvTensorMap* s1, const ConvTensorMap* s2, const ConvArgs& args,
+                       cudaStream_t stream) {
+  using L = SmemLayoutHalo<TWO, BN, AST, BST>;
+  constexpr int smem_bytes = L::TOTAL + 1024;
+  static_assert(smem_bytes <= 227 * 1024, "halo kernel shared memory budget");
+  auto kern = conv_halo_kernel<TWO, BN, AST, BST>;
+  static bool configured = false;
+  if (!configured) {
+    PDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    if (TWO) PDR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+    configured = true;
+  }
+  const int tiles_m = args.tiles_b * args.tiles_y * args.tiles_x;
+  const int work = (TWO ? tiles_m / 2 : tiles_m) * args.tiles_n;
+  const int units = TWO ? num_sms() / 2 : num_sms();
+  const int workers = work < units ? work : units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(TWO ? 2 * workers : workers);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = TWO ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PDR_CUDA(cudaLaunchKernelEx(&cfg, kern, *(const CUtensorMap*)a1,
+                              *(const CUtensorMap*)(a2 ? a2 : a1), *(const CUtensorMap*)w,
+                              *(const CUtensorMap*)(s1 ? s1 : a1),
+                              *(const CUtensorMap*)(s2 ? s2 : (s1 ? s1 : a1)), args));
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
 // BN == 512 selects the 2-CTA kernel (256-wide N tile per SM pair; the weight map must have been
 // encoded with a 128-row box)
 int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
                    int BN, int B, int H, int W, int C1, int C2, int Cout, int taps,
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
                    cudaStream_t stream, float qk_scale, const ConvTensorMap* s1,
-                   const ConvTensorMap* s2, int S1, int S2, int ksplit, float* splitk_ws) {
+                   const ConvTensorMap* s2, int S1, int S2, int ksplit, float* splitk_ws,
+                   int halo) {
+  PDR_CHECK_ARG(!halo || (conv_tc_halo_ok(H, W, taps) && ksplit == 1),
+                "halo mode needs a 3x3 conv on a map with W %% 8 == 0, H %% 16 == 0 and no split-K");
   PDR_CHECK_ARG(ksplit >= 1 && (ksplit == 1 || (splitk_ws != nullptr && BN != 512 &&
                                                 stats_partial == nullptr && qk_scale == 0.f)),
                 "split-K needs a workspace, a 1-CTA tile, and no fused statistics / qk scaling");
@@ -849,6 +1146,8 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   args.Cout = Cout;
   args.taps = taps;
   conv_tc_pick_box(B, H, W, &args.bw, &args.bh, &args.bb);
+  if (halo) args.bw = 8, args.bh = 16, args.bb = 1;
+  args.halo = halo;
   PDR_CHECK_ARG(args.bw * args.bh * args.bb == 128 && W % args.bw == 0 && H % args.bh == 0,
                 "unsupported spatial size %dx%d", H, W);
   args.tiles_x = W / args.bw;
@@ -869,7 +1168,13 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   if (two_cta) {
     PDR_CHECK_ARG((args.tiles_b * args.tiles_y * args.tiles_x) % 2 == 0,
                   "2-CTA conv needs an even number of 128-pixel tiles");
+    if (halo) return launch_halo<true, 256, 3, 9>(a1, a2, w, s1, s2, args, stream);
     return launch_impl2<6>(a1, a2, w, s1, s2, args, stream);
+  }
+  if (halo) {
+    if (BN == 256) return launch_halo<false, 256, 2, 5>(a1, a2, w, s1, s2, args, stream);
+    if (BN == 128) return launch_halo<false, 128, 3, 9>(a1, a2, w, s1, s2, args, stream);
+    return launch_halo<false, 64, 3, 12>(a1, a2, w, s1, s2, args, stream);
   }
   if (BN == 256) return launch_impl<256, 4>(a1, a2, w, s1, s2, args, stream);
   if (BN == 128) return launch_impl<128, 6>(a1, a2, w, s1, s2, args, stream);

@@ -18,7 +18,12 @@ void conv_tc_pick_box(int B, int H, int W, int* bw, int* bh, int* bb);
 int conv_tc_pick_bn(int B, int H, int W, int Cout);
 
 // NHWC fp16 activation [B,H,W,C], C % 64 == 0
-int conv_tc_make_act_map(ConvTensorMap* out, const void* ptr, int B, int H, int W, int C);
+// halo != 0: the box is the 10 x 18 pixel halo of an 8 x 16 output tile (conv_halo_kernel)
+int conv_tc_make_act_map(ConvTensorMap* out, const void* ptr, int B, int H, int W, int C,
+                         int halo = 0);
+// 3x3 convs on maps with W % 8 == 0 and H % 16 == 0 run the halo kernel: all nine taps of a
+// 64-channel chunk read ONE shared-memory tile (activation maps must be encoded with halo = 1)
+bool conv_tc_halo_ok(int H, int W, int taps);
 // fp16 weights [Cout][K] with K = taps*Cin ordered (tap, channel)
 int conv_tc_make_weight_map(ConvTensorMap* out, const void* ptr, int Cout, int K, int BN);
 
@@ -35,7 +40,7 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
                    cudaStream_t stream, float qk_scale = 0.f, const ConvTensorMap* s1 = nullptr,
                    const ConvTensorMap* s2 = nullptr, int S1 = 0, int S2 = 0, int ksplit = 1,
-                   float* splitk_ws = nullptr);
+                   float* splitk_ws = nullptr, int halo = 0);
 // split-K for layers with too few tiles to fill the GPU: returns the number of K ranges (1 = off)
 // for a layer with `num_k` 64-channel K steps and may change *bn; the workspace holds the fp32
 // partial tiles (conv_tc_split_workspace_bytes) and a finishing kernel applies the epilogue

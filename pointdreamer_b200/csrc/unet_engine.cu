@@ -293,14 +293,18 @@ class UnetEngine {
     if (dry_) return 0;
     ConvOp* c = new ConvOp();
     conv_ops.push_back(c);
-    PDR_TRY(conv_tc_make_act_map(&c->a1, P<__half>(x1.off), B_, x1.H, x1.W, x1.C));
-    if (x2) PDR_TRY(conv_tc_make_act_map(&c->a2, P<__half>(x2->off), B_, x2->H, x2->W, x2->C));
+    const int halo = ksplit == 1 && conv_tc_halo_ok(out.H, out.W, taps) ? 1 : 0;
+    PDR_TRY(conv_tc_make_act_map(&c->a1, P<__half>(x1.off), B_, x1.H, x1.W, x1.C, halo));
+    if (x2)
+      PDR_TRY(conv_tc_make_act_map(&c->a2, P<__half>(x2->off), B_, x2->H, x2->W, x2->C, halo));
     PDR_TRY(conv_tc_make_weight_map(&c->w, w->ptr, out.C, taps * Cin + Cs1 + Cs2,
                                     bn == 512 ? 128 : bn));
     if (skip1)
-      PDR_TRY(conv_tc_make_act_map(&c->s1, P<__half>(skip1->off), B_, skip1->H, skip1->W, Cs1));
+      PDR_TRY(conv_tc_make_act_map(&c->s1, P<__half>(skip1->off), B_, skip1->H, skip1->W, Cs1,
+                                   halo));
     if (skip2)
-      PDR_TRY(conv_tc_make_act_map(&c->s2, P<__half>(skip2->off), B_, skip2->H, skip2->W, Cs2));
+      PDR_TRY(conv_tc_make_act_map(&c->s2, P<__half>(skip2->off), B_, skip2->H, skip2->W, Cs2,
+                                   halo));
     const bool hs1 = skip1 != nullptr, hs2 = skip2 != nullptr;
     const int H = out.H, W = out.W, C1 = x1.C, C2 = x2 ? x2->C : 0, Co = out.C, Bn = B_;
     const float* bias = (const float*)b->ptr;
@@ -314,7 +318,7 @@ class UnetEngine {
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return conv_tc_launch(&c->a1, has2 ? &c->a2 : nullptr, &c->w, bn, Bn, H, W, C1, C2, Co, taps,
                             bias, r, o, partial, s, qk_scale, hs1 ? &c->s1 : nullptr,
-                            hs2 ? &c->s2 : nullptr, Cs1, Cs2, ksplit, split_ws);
+                            hs2 ? &c->s2 : nullptr, Cs1, Cs2, ksplit, split_ws, halo);
     });
     if (stat_rows > 0) {
       double* sums = P<double>(out.sums_off);
