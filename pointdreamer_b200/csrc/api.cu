@@ -20,7 +20,7 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
   PDR_CHECK_ARG(x1 && w && out, "pdr_conv_tc: null pointer");
   PDR_CHECK_ARG(B > 0 && H > 0 && W > 0, "pdr_conv_tc: empty shape");
   PDR_CHECK_ARG(Cout % 64 == 0, "pdr_conv_tc: Cout (%d) must be a multiple of 64", Cout);
-  if (bn == 0) bn = conv_tc_pick_bn(B, H, W, Cout);
+  if (bn == 0) bn = conv_tc_pick_bn(B, H, W, Cout, taps);
   ConvTensorMap ma1, ma2, mw;
   const int halo = conv_tc_halo_ok(H, W, taps) ? 1 : 0;
   PDR_TRY(conv_tc_make_act_map(&ma1, x1, B, H, W, C1, halo));
@@ -39,7 +39,7 @@ int pdr_conv_tc_skip(const void* x, const void* w, const float* bias, const void
                      int Cout, int bn, void* stream) {
   PDR_CHECK_ARG(x && w && s1 && out, "pdr_conv_tc_skip: null pointer");
   PDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && Cout % 64 == 0, "pdr_conv_tc_skip: bad shape");
-  if (bn == 0) bn = conv_tc_pick_bn(B, H, W, Cout);
+  if (bn == 0) bn = conv_tc_pick_bn(B, H, W, Cout, 9);
   ConvTensorMap ma, ms1, ms2, mw;
   const int halo = conv_tc_halo_ok(H, W, 9) ? 1 : 0;
   PDR_TRY(conv_tc_make_act_map(&ma, x, B, H, W, C, halo));

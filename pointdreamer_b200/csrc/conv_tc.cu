@@ -949,26 +949,33 @@ int conv_tc_stats_rows_per_image(int H, int W) {
   return (H / bh) * (W / bw) * 4;
 }
 
-int conv_tc_pick_bn(int B, int H, int W, int Cout) {
+int conv_tc_pick_bn(int B, int H, int W, int Cout, int taps) {
   // Returns the N tile with the lowest modelled time: 64 / 128 / 256 (1-CTA) or 512 = the 2-CTA
-  // kernel (256-wide tile per SM pair).  Model, fitted to the measured layer table
-  // (profiles/README.md): a k-step of a 128 x bn tile costs max(MMA time, TMA time) with
-  // MMA = bn * 1.078 ns (15.2 TFLOP/s per SM) and TMA = (128 + bn) * 128 B at ~150 GB/s per SM
-  // (the shared-memory fill rate a single CTA sustains from L2: bn = 64 / 128 / 256 reach
-  // 43 / 65 / 80 % of the tensor peak); the SM pair of the 2-CTA kernel stages half of the
-  // weight tile each and is MMA-bound (0.28 us per k-step of a 256 x 256 tile).  Time =
-  // waves over the 148 SMs (74 pairs) x k-step cost; K is common to all candidates.
+  // kernel (256-wide tile per SM pair).  Time = waves over the 148 SMs (74 pairs) x cost of one
+  // k-step of the tile; K is common to all candidates.  k-step costs (us), fitted to the measured
+  // layer tables in profiles/README.md:
+  //  * plain kernels: max(MMA, TMA) with MMA = bn * 1.078 ns (15.2 TFLOP/s per SM) and TMA =
+  //    (128 + bn) * 128 B at ~150 GB/s per SM, the shared-memory fill rate one CTA sustains from
+  //    L2 (bn = 64 / 128 / 256 reach 43 / 65 / 80 % of the tensor peak); SM pair 0.285;
+  //  * halo kernels (3x3, maps >= 16 x 8): the activation tile is filled once per nine k-steps, so
+  //    every tile is MMA-bound; measured efficiencies 53 / 80 / 88 % (1-CTA) and 96 % (pair).
   int bw, bh, bb;
   conv_tc_pick_box(B, H, W, &bw, &bh, &bb);
+  const bool halo = conv_tc_halo_ok(H, W, taps);
+  if (halo) bb = 1, bw = 8, bh = 16;
   const long long tiles_m = (long long)cdiv(B, bb) * (H / bh) * (W / bw);
   const int sms = num_sms();
+  auto kstep = [halo](int bn) {
+    if (halo) return bn == 64 ? 0.130 : (bn == 128 ? 0.1725 : 0.3136);
+    const double mma = bn * 1.078e-3, tma = (128 + bn) * 0.853e-3;
+    return mma > tma ? mma : tma;
+  };
   int best = 0;
   double best_cost = 1e30;
   for (int bn = 256; bn >= 64; bn >>= 1) {
     if (Cout % bn != 0) continue;
     const long long tiles = tiles_m * (Cout / bn);
-    const double mma = bn * 1.078e-3, tma = (128 + bn) * 0.853e-3;
-    const double cost = (double)cdiv(tiles, sms) * (mma > tma ? mma : tma);
+    const double cost = (double)cdiv(tiles, sms) * kstep(bn);
     if (cost < best_cost * 0.98) {  // prefer the larger tile on a tie (less L2 traffic)
       best_cost = cost;
       best = bn;
@@ -976,7 +983,7 @@ int conv_tc_pick_bn(int B, int H, int W, int Cout) {
   }
   if (Cout % 256 == 0 && tiles_m % 2 == 0) {
     const long long pairs = (tiles_m / 2) * (Cout / 256);
-    const double cost = (double)cdiv(pairs, sms / 2) * 0.285;
+    const double cost = (double)cdiv(pairs, sms / 2) * (halo ? 0.2875 : 0.285);
     if (cost < best_cost * 0.98) best = 512;
   }
   return best;

@@ -15,7 +15,7 @@ struct alignas(64) ConvTensorMap {
 void conv_tc_pick_box(int B, int H, int W, int* bw, int* bh, int* bb);
 // N tile that keeps all SMs busy for this layer: 64 / 128 / 256, or 512 = the 2-CTA kernel
 // (cta_group::2, 256-wide tile per SM pair; its weight map uses a 128-row box)
-int conv_tc_pick_bn(int B, int H, int W, int Cout);
+int conv_tc_pick_bn(int B, int H, int W, int Cout, int taps = 1);
 
 // NHWC fp16 activation [B,H,W,C], C % 64 == 0
 // halo != 0: the box is the 10 x 18 pixel halo of an 8 x 16 output tile (conv_halo_kernel)

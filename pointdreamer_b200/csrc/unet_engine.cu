@@ -281,7 +281,7 @@ class UnetEngine {
     }
     // tile + split-K choice; the split-K partial tiles share the statistics scratch (a conv has
     // one or the other, and its consumer kernel follows it on the stream)
-    int bn = conv_tc_pick_bn(B_, out.H, out.W, out.C);
+    int bn = conv_tc_pick_bn(B_, out.H, out.W, out.C, taps);
     int ksplit = 1;
     if (stat_rows == 0 && qk_scale == 0.f && taps == 9) {
       // decided for a FIXED reference batch of 8: splitting changes the fp32 summation order, and
