@@ -332,7 +332,7 @@ def main():
     roofline = {
         "bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": conv_tflops / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
-        "kernel": "conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv, 2-CTA and 1-CTA)",
+        "kernel": "conv_halo_kernel / conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv: halo-tile 3x3, 2-CTA and 1-CTA)",
         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
         "launch_avg_ms": conv["ms"] / max(conv["launches"], 1),
         "flops_per_launch_avg": conv["flops"] / max(conv["launches"], 1),

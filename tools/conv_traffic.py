@@ -16,7 +16,7 @@ for r in rows:
     elif r[-3].startswith("gpu__time"):
         v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0}[unit]
     d[r[-3]] = v
-launches = [d for d in per.values() if "conv_tc" in d["name"]]  # split-K finish folded in below
+launches = [d for d in per.values() if "conv_tc" in d["name"] or "conv_halo" in d["name"]]  # split-K finish folded in below
 finish = [d for d in per.values() if "splitk_finish" in d["name"]]
 rd = sum(d.get("dram__bytes_read.sum", 0) for d in launches + finish)
 wr = sum(d.get("dram__bytes_write.sum", 0) for d in launches + finish)
