@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "conv_tc.h"
+#include "gn_math.cuh"
 
 namespace pdr {
 
@@ -52,6 +53,11 @@ struct ConvArgs {
   int ksplit;
   float* splitk_ws;
   int halo;  // 1: conv_halo_kernel (8 x 16 pixel tiles, activation maps encoded with the halo box)
+  // halo kernel only: GroupNorm32 (+FiLM) + SiLU of the conv INPUT applied in shared memory by the
+  // transform warps (the A maps then point at the raw tensor): float4 (ga, gb, fs, fsh) per
+  // (image, input channel of cat(A1, A2)); null = the input is already activated
+  const float4* gn_coeff;
+  int gn_film;
 };
 
 template <int BN, int STAGES>
@@ -658,12 +664,15 @@ struct SmemLayoutHalo {
   static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int B_OFFSET = AST * HALO_STAGE;
   static constexpr int BAR_OFFSET = B_OFFSET + BST * B_BYTES;
-  // a_full[AST], a_empty[AST], b_full[BST], b_empty[BST], tmem_full[2], tmem_empty[2], tmem ptr
-  static constexpr int TOTAL = BAR_OFFSET + (2 * AST + 2 * BST + 4) * 8 + 16;
+  // a_full[AST], a_empty[AST], a_ready[AST], b_full[BST], b_empty[BST], tmem_full[2],
+  // tmem_empty[2], tmem ptr
+  static constexpr int TOTAL = BAR_OFFSET + (3 * AST + 2 * BST + 4) * 8 + 16;
 };
 
+static constexpr int HALO_THREADS = 384;  // 8 warps as in the plain kernels + 4 transform warps
+
 template <bool TWO, int BN, int AST, int BST>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmS1,
                  const __grid_constant__ CUtensorMap tmS2, const ConvArgs args) {
@@ -672,7 +681,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* a_full = (uint64_t*)(smem + L::BAR_OFFSET);
   uint64_t* a_empty = a_full + AST;
-  uint64_t* b_full = a_empty + AST;
+  uint64_t* a_ready = a_empty + AST;  // fused GroupNorm: the transform warps' "tile activated"
+  uint64_t* b_full = a_ready + AST;
   uint64_t* b_empty = b_full + BST;
   uint64_t* tmem_full = b_empty + BST;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -692,6 +702,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int num_workers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr uint32_t TXMUL = TWO ? 2u : 1u;  // the leader's barrier counts the bytes of both CTAs
+  // fused GroupNorm: every CTA's halo lands on its OWN a_full (its transform warps wait there), the
+  // MMA issuer waits on a_ready, which the transform warps of both CTAs of a pair arrive on
+  const bool fused = args.gn_coeff != nullptr;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
@@ -702,6 +715,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int i = 0; i < AST; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
+      mbar_init(&a_ready[i], TWO ? 8 : 4);  // one arrive per transform warp (of both CTAs)
     }
     for (int i = 0; i < BST; ++i) {
       mbar_init(&b_full[i], 1);
@@ -745,7 +759,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const bool main_chunk = ch < chunks_main;
           mbar_wait(&a_empty[as], aph ^ 1);
           uint8_t* sa = smem + as * HALO_STAGE;
-          if (leader) mbar_expect_tx(&a_full[as], TXMUL * HALO_BYTES);
+          if (fused)
+            mbar_expect_tx(&a_full[as], HALO_BYTES);
+          else if (leader)
+            mbar_expect_tx(&a_full[as], TXMUL * HALO_BYTES);
           int c = (main_chunk ? ch : ch - chunks_main) * BLOCK_K;
           const CUtensorMap* tm;
           if (main_chunk) {
@@ -755,7 +772,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             tm = c < args.S1 ? &tmS1 : &tmS2;
             if (c >= args.S1) c -= args.S1;
           }
-          if (TWO)
+          if (TWO && !fused)
             tma2_load_4d(sa, tm, &a_full[as], c, x0, y0, tb);
           else
             tma_load_4d(sa, tm, &a_full[as], c, x0, y0, tb);
@@ -795,7 +812,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         uint32_t first = 1;
         for (int ch = 0; ch < chunks_all; ++ch) {
-          mbar_wait(&a_full[as], aph);
+          mbar_wait(fused ? &a_ready[as] : &a_full[as], aph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + as * HALO_STAGE);
           const int ntaps = ch < chunks_main ? 9 : 1;
@@ -835,6 +852,58 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       }
     }
     __syncwarp();
+  } else if (warp >= 8) {
+    // ==================================== transform warps (fused GroupNorm) ====
+    // GroupNorm32 (+FiLM) + SiLU of the raw halo tile, in place, once per chunk: thread = fixed
+    // 8-channel group (its 8 x (ga, gb, fs, fsh) live in registers for the chunk), rows strided
+    // by 16; pixels outside the image stay zero (the conv pads the ACTIVATED tensor).
+    if (fused) {
+      const int tt = threadIdx.x - 256;          // 0..127
+      const int lc = tt & 7, row0 = tt >> 3;     // logical 16-byte chunk, first halo row
+      const bool film = args.gn_film != 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int work = worker; work < num_work; work += num_workers) {
+        int m_tile = TWO ? (work / args.tiles_n) * 2 + (int)rank : work / args.tiles_n;
+        const int tx = m_tile % args.tiles_x;
+        m_tile /= args.tiles_x;
+        const int ty = m_tile % args.tiles_y;
+        const int tb = m_tile / args.tiles_y;
+        const int x0 = tx * 8 - 1, y0 = ty * 16 - 1;
+        for (int ch = 0; ch < chunks_all; ++ch) {
+          mbar_wait(&a_full[as], aph);
+          if (ch < chunks_main) {
+            float4 cf[8];
+            const float4* cp = args.gn_coeff + (size_t)tb * Ctot + ch * BLOCK_K + lc * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cf[j] = __ldg(cp + j);
+            uint8_t* sa = smem + as * HALO_STAGE;
+            for (int r = row0; r < HALO_W * HALO_H; r += 16) {
+              const int hy = r / HALO_W, hx = r - hy * HALO_W;
+              const int gy = y0 + hy, gx = x0 + hx;
+              if (gy < 0 || gy >= args.H || gx < 0 || gx >= args.W) continue;
+              uint4* p = (uint4*)(sa + r * 128 + ((lc ^ (r & 7)) << 4));
+              uint4 v = *p;
+              __half* h = (__half*)&v;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                h[j] = __float2half_rn(gn_apply_one(__half2float(h[j]), cf[j].x, cf[j].y, cf[j].z,
+                                                    cf[j].w, film, true));
+              *p = v;
+            }
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's reads
+          __syncwarp();
+          if (lane == 0) {
+            if (TWO) mbar_arrive_cluster(&a_ready[as], 0); else mbar_arrive(&a_ready[as]);
+          }
+          if (++as == AST) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+      }
+    }
   } else if (warp >= 4) {
     // ========================================================= epilogue ====
     const int q = warp & 3;
@@ -1098,7 +1167,7 @@ static int launch_halo(const ConvTensorMap* a1, const ConvTensorMap* a2, const C
   const int workers = work < units ? work : units;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(TWO ? 2 * workers : workers);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(HALO_THREADS);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1124,7 +1193,8 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
                    cudaStream_t stream, float qk_scale, const ConvTensorMap* s1,
                    const ConvTensorMap* s2, int S1, int S2, int ksplit, float* splitk_ws,
-                   int halo) {
+                   int halo, const float4* gn_coeff, int gn_film) {
+  PDR_CHECK_ARG(gn_coeff == nullptr || halo, "a fused GroupNorm needs the halo kernel");
   PDR_CHECK_ARG(!halo || (conv_tc_halo_ok(H, W, taps) && ksplit == 1),
                 "halo mode needs a 3x3 conv on a map with W %% 8 == 0, H %% 16 == 0 and no split-K");
   PDR_CHECK_ARG(ksplit >= 1 && (ksplit == 1 || (splitk_ws != nullptr && BN != 512 &&
@@ -1155,6 +1225,8 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   conv_tc_pick_box(B, H, W, &args.bw, &args.bh, &args.bb);
   if (halo) args.bw = 8, args.bh = 16, args.bb = 1;
   args.halo = halo;
+  args.gn_coeff = gn_coeff;
+  args.gn_film = gn_film;
   PDR_CHECK_ARG(args.bw * args.bh * args.bb == 128 && W % args.bw == 0 && H % args.bh == 0,
                 "unsupported spatial size %dx%d", H, W);
   args.tiles_x = W / args.bw;

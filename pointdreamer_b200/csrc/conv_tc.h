@@ -40,7 +40,11 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
                    cudaStream_t stream, float qk_scale = 0.f, const ConvTensorMap* s1 = nullptr,
                    const ConvTensorMap* s2 = nullptr, int S1 = 0, int S2 = 0, int ksplit = 1,
-                   float* splitk_ws = nullptr, int halo = 0);
+                   float* splitk_ws = nullptr, int halo = 0, const float4* gn_coeff = nullptr,
+                   int gn_film = 0);
+// gn_coeff (halo kernel only): the A maps point at the RAW tensor and GroupNorm32 (+FiLM when
+// gn_film) + SiLU is applied to each halo tile in shared memory with the constants of
+// gn_coeff_launch (unet_ops.h): float4 (ga, gb, fs, fsh) per (image, channel of cat(A1, A2))
 // split-K for layers with too few tiles to fill the GPU: returns the number of K ranges (1 = off)
 // for a layer with `num_k` 64-channel K steps and may change *bn; the workspace holds the fp32
 // partial tiles (conv_tc_split_workspace_bytes) and a finishing kernel applies the epilogue

@@ -1,0 +1,25 @@
+// The per-element arithmetic of GroupNorm32 (+FiLM) (+SiLU) on an fp16 activation, shared by
+// gn_apply_kernel (unet_ops.cu) and the transform warps of conv_halo_kernel (conv_tc.cu) so both
+// produce the same bits.  Reference rounding points: GroupNorm32 computes in fp32 and casts back
+// (nn.py:17-19), h * (1 + scale) + shift and SiLU are fp16 tensor ops (unet.py:248-252).
+#pragma once
+#include <cuda_fp16.h>
+
+namespace pdr {
+
+__device__ __forceinline__ float gnm_round_h(float x) { return __half2float(__float2half_rn(x)); }
+// SiLU whose result is immediately rounded to fp16: ex2.approx / rcp.approx (abs error ~1e-6)
+__device__ __forceinline__ float gnm_silu_fast(float x) {
+  return __fdividef(x, 1.0f + __expf(-x));
+}
+// x: fp16 value as float; ga/gb: GroupNorm affine (rstd*gamma, beta - mean*rstd*gamma);
+// fs/fsh: FiLM (1+scale) and shift, both fp16 values as float
+__device__ __forceinline__ float gn_apply_one(float x, float ga, float gb, float fs, float fsh,
+                                              bool film, bool silu) {
+  float t = gnm_round_h(x * ga + gb);
+  if (film) t = gnm_round_h(gnm_round_h(t * fs) + fsh);
+  if (silu) t = gnm_round_h(gnm_silu_fast(t));
+  return t;
+}
+
+}  // namespace pdr

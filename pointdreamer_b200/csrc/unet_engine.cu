@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "conv_tc.h"
 #include "unet_ops.h"
+#include <stdlib.h>
 #include "unet_engine.h"
 
 namespace pdr {
@@ -179,6 +180,9 @@ class UnetEngine {
   int B_ = 0;
   size_t off_stats_[2] = {0, 0}, off_gnws_ = 0, off_e1_ = 0, off_emb_ = 0, off_emb16_ = 0;
   size_t off_partial_ = 0, partial_bytes_ = 0, partial_reserved_ = 0;
+  // GroupNorm + SiLU fused into the halo conv's transform warps; PDR_NO_FUSED_GN=1 (read at every
+  // plan) keeps the separate gn_apply pass - both paths produce the same bits
+  bool fuse_gn_ = true;
 
  public:
   size_t off_tcur_ = 0;  // float[B]: the timestep the captured graph reads
@@ -258,10 +262,35 @@ class UnetEngine {
     return 0;
   }
 
+  // GroupNorm applied INSIDE the consuming conv (halo kernel): only the per-(image, channel)
+  // constants are materialised.  Returns the arena offset of the float4[B][C] table in *coeff_off.
+  int add_gn_coeff(const Act& x1, const Act* x2, const std::string& pname, int which, bool film,
+                   int film_off, size_t* coeff_off) {
+    const int C = x1.C + (x2 ? x2->C : 0);
+    *coeff_off = pl_.alloc((size_t)B_ * C * sizeof(float4));
+    if (dry_) return 0;
+    const float* g = (const float*)find(pname + ".weight", (size_t)C * 4)->ptr;
+    const float* b = (const float*)find(pname + ".bias", (size_t)C * 4)->ptr;
+    const int H = x1.H, W = x1.W, C1 = x1.C, C2 = x2 ? x2->C : 0, Bn = B_;
+    const float* st = P<float>(off_stats_[which]);
+    const bool from_sums = x1.has_sums && (!x2 || x2->has_sums) && C % 256 == 0;
+    const double* s1 = from_sums ? P<double>(x1.sums_off) : nullptr;
+    const double* s2 = from_sums && x2 ? P<double>(x2->sums_off) : nullptr;
+    const __half* fl = film ? P<__half>(off_emb16_) : nullptr;
+    const int fstride = emb_total_;
+    float4* co = P<float4>(*coeff_off);
+    ops.cur_cls = PDR_OP_GN_APPLY;
+    ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
+      return gn_coeff_launch(Bn, H, W, C1, C2, from_sums ? nullptr : st, s1, s2, g, b, fl, fstride,
+                             film_off, co, s);
+    });
+    return 0;
+  }
+
   // want_sums: also produce the GroupNorm sums of `out` in the epilogue (when the tile allows)
   int add_conv(const Act& x1, const Act* x2, const std::string& pname, int taps, const Act* res,
                Act& out, bool want_sums = false, float qk_scale = 0.f, const Act* skip1 = nullptr,
-               const Act* skip2 = nullptr) {
+               const Act* skip2 = nullptr, const size_t* gn_coeff_off = nullptr, int gn_film = 0) {
     const int stat_rows = want_sums && out.C % 256 == 0 ? conv_tc_stats_rows_per_image(out.H, out.W) : 0;
     if (stat_rows > 0) {
       out.has_sums = true;
@@ -283,7 +312,7 @@ class UnetEngine {
     // one or the other, and its consumer kernel follows it on the stream)
     int bn = conv_tc_pick_bn(B_, out.H, out.W, out.C, taps);
     int ksplit = 1;
-    if (stat_rows == 0 && qk_scale == 0.f && taps == 9) {
+    if (stat_rows == 0 && qk_scale == 0.f && taps == 9 && !gn_coeff_off) {
       // decided for a FIXED reference batch of 8: splitting changes the fp32 summation order, and
       // a chain's bits must not depend on the batch it happens to run in
       ksplit = conv_tc_pick_split(8, out.H, out.W, out.C, taps * (Cin / 64) + (Cs1 + Cs2) / 64, &bn);
@@ -294,6 +323,11 @@ class UnetEngine {
     ConvOp* c = new ConvOp();
     conv_ops.push_back(c);
     const int halo = ksplit == 1 && conv_tc_halo_ok(out.H, out.W, taps) ? 1 : 0;
+    if (gn_coeff_off && !halo) {
+      set_error("internal: fused GroupNorm requested for a conv that does not run the halo kernel");
+      return -1;
+    }
+    const float4* coeff = gn_coeff_off ? P<float4>(*gn_coeff_off) : nullptr;
     PDR_TRY(conv_tc_make_act_map(&c->a1, P<__half>(x1.off), B_, x1.H, x1.W, x1.C, halo));
     if (x2)
       PDR_TRY(conv_tc_make_act_map(&c->a2, P<__half>(x2->off), B_, x2->H, x2->W, x2->C, halo));
@@ -318,7 +352,8 @@ class UnetEngine {
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return conv_tc_launch(&c->a1, has2 ? &c->a2 : nullptr, &c->w, bn, Bn, H, W, C1, C2, Co, taps,
                             bias, r, o, partial, s, qk_scale, hs1 ? &c->s1 : nullptr,
-                            hs2 ? &c->s2 : nullptr, Cs1, Cs2, ksplit, split_ws, halo);
+                            hs2 ? &c->s2 : nullptr, Cs1, Cs2, ksplit, split_ws, halo, coeff,
+                            gn_film);
     });
     if (stat_rows > 0) {
       double* sums = P<double>(out.sums_off);
@@ -340,8 +375,17 @@ class UnetEngine {
     emb_cursor_ += 2 * Cout;
     // in_layers: GN + SiLU (+ resample) -> conv
     PDR_TRY(add_gn(x1, x2, p + ".in_layers.0", 0, nullptr));
-    Act a1 = new_act(Ho, Wo, Cin);
-    PDR_TRY(add_gn_apply(x1, x2, p + ".in_layers.0", 0, false, 0, true, resample, a1));
+    // GroupNorm + SiLU of the block input applied inside in_layers.2's halo kernel (no activated
+    // copy of the input in HBM) when nothing is resampled in between
+    const bool fuse1 = fuse_gn_ && !resample && conv_tc_halo_ok(Ho, Wo, 9);
+    size_t coeff1 = 0;
+    Act a1;
+    if (fuse1) {
+      PDR_TRY(add_gn_coeff(x1, x2, p + ".in_layers.0", 0, false, 0, &coeff1));
+    } else {
+      a1 = new_act(Ho, Wo, Cin);
+      PDR_TRY(add_gn_apply(x1, x2, p + ".in_layers.0", 0, false, 0, true, resample, a1));
+    }
     Act xr;
     bool have_xr = false;
     if (resample) {
@@ -362,24 +406,40 @@ class UnetEngine {
       }
     }
     Act h1 = new_act(Ho, Wo, Cout);
-    PDR_TRY(add_conv(a1, nullptr, p + ".in_layers.2", 9, nullptr, h1, true));
-    drop(a1);
+    if (fuse1) {
+      PDR_TRY(add_conv(x1, x2, p + ".in_layers.2", 9, nullptr, h1, true, 0.f, nullptr, nullptr,
+                       &coeff1, 0));
+      pl_.release(coeff1);
+    } else {
+      PDR_TRY(add_conv(a1, nullptr, p + ".in_layers.2", 9, nullptr, h1, true));
+      drop(a1);
+    }
     // out_layers: GN * (1+scale) + shift, SiLU, conv (+ skip)
     PDR_TRY(add_gn(h1, nullptr, p + ".out_layers.0", 1, nullptr));
-    Act a2 = new_act(Ho, Wo, Cout);
-    PDR_TRY(add_gn_apply(h1, nullptr, p + ".out_layers.0", 1, true, film_off, true, 0, a2));
-    drop(h1);
+    const bool fuse2 = fuse_gn_ && conv_tc_halo_ok(Ho, Wo, 9);
+    size_t coeff2 = 0;
+    Act a2;
+    if (fuse2) {
+      PDR_TRY(add_gn_coeff(h1, nullptr, p + ".out_layers.0", 1, true, film_off, &coeff2));
+      a2 = h1;  // out_layers.3 reads the raw conv output and activates it tile by tile
+    } else {
+      a2 = new_act(Ho, Wo, Cout);
+      PDR_TRY(add_gn_apply(h1, nullptr, p + ".out_layers.0", 1, true, film_off, true, 0, a2));
+      drop(h1);
+    }
     Act out = new_act(Ho, Wo, Cout);
     if (Cin != Cout) {
       // channel-changing block: skip_connection (1x1) rides in the K loop of out_layers.3 -
       // "<p>.out_layers.3_skip" = [w3x3 | w1x1] along K, biases summed (set by the host side)
       const Act& sx = have_xr ? xr : x1;
       PDR_TRY(add_conv(a2, nullptr, p + ".out_layers.3_skip", 9, nullptr, out, true, 0.f, &sx,
-                       have_xr ? nullptr : x2));
+                       have_xr ? nullptr : x2, fuse2 ? &coeff2 : nullptr, 1));
     } else {
       Act skip = have_xr ? xr : x1;
-      PDR_TRY(add_conv(a2, nullptr, p + ".out_layers.3", 9, &skip, out, true));
+      PDR_TRY(add_conv(a2, nullptr, p + ".out_layers.3", 9, &skip, out, true, 0.f, nullptr, nullptr,
+                       fuse2 ? &coeff2 : nullptr, 1));
     }
+    if (fuse2) pl_.release(coeff2);
     drop(a2);
     if (have_xr) drop(xr);
     *result = out;
@@ -425,6 +485,7 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
   clear_plan();
   pl_ = Planner();
   dry_ = dry;
+  fuse_gn_ = getenv("PDR_NO_FUSED_GN") == nullptr;
   B_ = B;
   arena = (uint8_t*)workspace;
   arena_bytes = ws_bytes;

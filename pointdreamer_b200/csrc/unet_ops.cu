@@ -9,6 +9,7 @@
 // the points where the reference materialises an fp16 tensor (see oracle/unet.py).
 #include "common.cuh"
 #include "unet_ops.h"
+#include "gn_math.cuh"
 
 namespace pdr {
 
@@ -523,10 +524,7 @@ __device__ __forceinline__ void gn_transform_8(const uint4& v, const float (&ga)
   const __half* h = (const __half*)&v;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float t = round_h(h2f(h[j]) * ga[j] + gb[j]);        // GroupNorm32 output, fp16
-    if (film) t = round_h(round_h(t * fs[j]) + fsh[j]);  // h*(1+scale) -> fp16, +shift -> fp16
-    if (silu) t = round_h(silu_fast(t));
-    y[j] = t;
+    y[j] = gn_apply_one(h2f(h[j]), ga[j], gb[j], fs[j], fsh[j], film, silu);  // gn_math.cuh
   }
 }
 __device__ __forceinline__ uint4 pack_8(const float (&y)[8]) {
@@ -647,6 +645,64 @@ gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
         *(uint4*)(dst + ((size_t)(2 * yi + (u >> 1)) * Wo + 2 * xi + (u & 1)) * C) = o;
     }
   }
+}
+
+// Per-(image, channel) constants of a GroupNorm32 (+FiLM) whose application is fused into the
+// consuming conv (conv_halo_kernel's transform warps): coeff[b][c] = (ga, gb, fs, fsh), the same
+// values gn_apply_kernel keeps in registers.  thread = (b, c).
+__global__ void gn_coeff_kernel(const GnApplyArgs a, float4* __restrict__ coeff) {
+  const int C = a.C1 + a.C2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.B * C) return;
+  const int b = i / C, c = i - b * C;
+  const int cpg = C / 32, g = c / cpg;
+  float mean, rstd;
+  if (a.sums1) {
+    double s = 0.0, q = 0.0;
+    for (int cc = g * cpg; cc < (g + 1) * cpg; cc += 8) {
+      const double* src = cc < a.C1 ? a.sums1 + ((size_t)b * (a.C1 / 8) + cc / 8) * 2
+                                    : a.sums2 + ((size_t)b * (a.C2 / 8) + (cc - a.C1) / 8) * 2;
+      s += src[0];
+      q += src[1];
+    }
+    const double cnt = (double)a.H * a.W * cpg;
+    const double m = s / cnt;
+    double var = q / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + 1e-5));
+  } else {
+    mean = a.stats[((size_t)b * 32 + g) * 2];
+    rstd = a.stats[((size_t)b * 32 + g) * 2 + 1];
+  }
+  const float ga = rstd * a.gamma[c];
+  const float gb = a.beta[c] - mean * ga;
+  float fs = 1.f, fsh = 0.f;
+  if (a.film) {
+    const __half* f = a.film + (size_t)b * a.film_stride + a.film_off;
+    fs = round_h(1.0f + h2f(f[c]));
+    fsh = h2f(f[C + c]);
+  }
+  coeff[i] = make_float4(ga, gb, fs, fsh);
+}
+
+int gn_coeff_launch(int B, int H, int W, int C1, int C2, const float* stats, const double* sums1,
+                    const double* sums2, const float* gamma, const float* beta, const __half* film,
+                    int film_stride, int film_off, float4* coeff, cudaStream_t stream) {
+  const int C = C1 + C2;
+  PDR_CHECK_ARG(C % 32 == 0 && (stats || sums1), "gn_coeff: bad arguments");
+  PDR_CHECK_ARG(!sums1 || C % 256 == 0, "gn_coeff from sums needs 8-aligned groups");
+  GnApplyArgs a;
+  a.x1 = a.x2 = nullptr;
+  a.C1 = C1, a.C2 = C2, a.B = B, a.H = H, a.W = W;
+  a.stats = stats, a.gamma = gamma, a.beta = beta;
+  a.sums1 = sums1, a.sums2 = sums2 ? sums2 : sums1;
+  a.film = film, a.film_stride = film_stride, a.film_off = film_off;
+  a.silu = 1, a.resample = 0, a.out = nullptr;
+  gn_coeff_kernel<<<cdiv((long long)B * C, 256), 256, 0, stream>>>(a, coeff);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
 }
 
 int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int C1, int C2,

@@ -107,3 +107,33 @@ def test_engine_full_size_vs_oracle(cuda):
           f"out std {o16.std():.3f}")
     assert np.isfinite(y).all()
     assert rel < 3e-3 and np.abs(y - o16).max() < 2e-2
+
+
+def test_fused_groupnorm_equals_separate_pass_bitwise(cuda):
+    """GroupNorm+SiLU applied by the halo conv's transform warps (default) vs the separate gn_apply
+    pass (PDR_NO_FUSED_GN=1, read at plan time): same arithmetic per element, same accumulation
+    order in the conv -> identical output bits, on a model with FiLM, skip convs and two-source
+    (concatenated) inputs."""
+    import os
+    from pointdreamer_b200.unet import UNetEngine, random_state_dict
+    cfg = dict(image_size=64, in_channels=3, model_channels=128, out_channels=6, num_res_blocks=2,
+               attention_resolutions="16,8", channel_mult=(1, 2, 2), num_head_channels=64,
+               num_heads=4, use_scale_shift_norm=True, resblock_updown=True, use_fp16=True,
+               use_new_attention_order=False)
+    sd = random_state_dict(cfg, 11, cuda)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(3, 3, 64, 64, generator=g).to(cuda)
+    t = torch.tensor([10.0, 500.0, 990.0], device=cuda)
+    outs = []
+    for no_fuse in (False, True):
+        if no_fuse:
+            os.environ["PDR_NO_FUSED_GN"] = "1"
+        else:
+            os.environ.pop("PDR_NO_FUSED_GN", None)
+        try:
+            eng = UNetEngine(sd, cfg, device=cuda)
+            outs.append(eng(x, t).clone())
+        finally:
+            os.environ.pop("PDR_NO_FUSED_GN", None)
+    assert torch.isfinite(outs[0]).all() and outs[0].abs().max() > 0
+    assert torch.equal(outs[0], outs[1])
