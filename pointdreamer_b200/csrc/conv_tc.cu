@@ -669,7 +669,8 @@ struct SmemLayoutHalo {
   static constexpr int TOTAL = BAR_OFFSET + (3 * AST + 2 * BST + 4) * 8 + 16;
 };
 
-static constexpr int HALO_THREADS = 384;  // 8 warps as in the plain kernels + 4 transform warps
+static constexpr int HALO_TWARPS = 8;                         // transform warps (fused GroupNorm)
+static constexpr int HALO_THREADS = 256 + 32 * HALO_TWARPS;  // 8 warps as in the plain kernels + them
 
 template <bool TWO, int BN, int AST, int BST>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
@@ -715,7 +716,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int i = 0; i < AST; ++i) {
       mbar_init(&a_full[i], 1);
       mbar_init(&a_empty[i], 1);
-      mbar_init(&a_ready[i], TWO ? 8 : 4);  // one arrive per transform warp (of both CTAs)
+      mbar_init(&a_ready[i], TWO ? 2 * HALO_TWARPS : HALO_TWARPS);  // one arrive per transform warp
     }
     for (int i = 0; i < BST; ++i) {
       mbar_init(&b_full[i], 1);
@@ -858,8 +859,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     // 8-channel group (its 8 x (ga, gb, fs, fsh) live in registers for the chunk), rows strided
     // by 16; pixels outside the image stay zero (the conv pads the ACTIVATED tensor).
     if (fused) {
-      const int tt = threadIdx.x - 256;          // 0..127
+      constexpr int RSTEP = 4 * HALO_TWARPS;                      // rows between a thread's rows
+      constexpr int NROWS = (HALO_W * HALO_H + RSTEP - 1) / RSTEP;
+      static_assert(RSTEP % 8 == 0, "the swizzle term (row & 7) must be constant per thread");
+      const int tt = threadIdx.x - 256;          // 0 .. 32*HALO_TWARPS-1
       const int lc = tt & 7, row0 = tt >> 3;     // logical 16-byte chunk, first halo row
+      const uint32_t toff = (uint32_t)row0 * 128u + (uint32_t)((lc ^ (row0 & 7)) << 4);
       const bool film = args.gn_film != 0;
       int as = 0;
       uint32_t aph = 0;
@@ -870,25 +875,45 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         const int ty = m_tile % args.tiles_y;
         const int tb = m_tile / args.tiles_y;
         const int x0 = tx * 8 - 1, y0 = ty * 16 - 1;
+        uint32_t vmask = 0;  // which of this thread's rows are pixels inside the image
+#pragma unroll
+        for (int i = 0; i < NROWS; ++i) {
+          const int r = row0 + i * RSTEP;
+          const int hy = r / HALO_W, hx = r - hy * HALO_W;
+          const int gy = y0 + hy, gx = x0 + hx;
+          if (r < HALO_W * HALO_H && gy >= 0 && gy < args.H && gx >= 0 && gx < args.W)
+            vmask |= 1u << i;
+        }
         for (int ch = 0; ch < chunks_all; ++ch) {
-          mbar_wait(&a_full[as], aph);
-          if (ch < chunks_main) {
-            float4 cf[8];
+          float2 ga[4], gb[4], fsh[4];
+          __half2 fs[4];
+          if (ch < chunks_main) {  // constants of this thread's 8 channels (L1-resident table)
             const float4* cp = args.gn_coeff + (size_t)tb * Ctot + ch * BLOCK_K + lc * 8;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cf[j] = __ldg(cp + j);
-            uint8_t* sa = smem + as * HALO_STAGE;
-            for (int r = row0; r < HALO_W * HALO_H; r += 16) {
-              const int hy = r / HALO_W, hx = r - hy * HALO_W;
-              const int gy = y0 + hy, gx = x0 + hx;
-              if (gy < 0 || gy >= args.H || gx < 0 || gx >= args.W) continue;
-              uint4* p = (uint4*)(sa + r * 128 + ((lc ^ (r & 7)) << 4));
-              uint4 v = *p;
-              __half* h = (__half*)&v;
+            for (int j = 0; j < 4; ++j) {
+              const float4 c0 = __ldg(cp + 2 * j), c1 = __ldg(cp + 2 * j + 1);
+              ga[j] = make_float2(c0.x, c1.x);
+              gb[j] = make_float2(c0.y, c1.y);
+              fs[j] = __floats2half2_rn(c0.z, c1.z);  // fp16 values: exact
+              fsh[j] = make_float2(c0.w, c1.w);
+            }
+          }
+          mbar_wait(&a_full[as], aph);
+          if (ch < chunks_main) {
+            uint8_t* base = smem + as * HALO_STAGE + toff;
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                h[j] = __float2half_rn(gn_apply_one(__half2float(h[j]), cf[j].x, cf[j].y, cf[j].z,
-                                                    cf[j].w, film, true));
+            for (int i = 0; i < NROWS; ++i) {
+              if (!((vmask >> i) & 1u)) continue;
+              uint4* p = (uint4*)(base + i * RSTEP * 128);
+              uint4 v = *p;
+              __half2* h = (__half2*)&v;
+              if (film) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = gn_apply_two<true>(h[j], ga[j], gb[j], fs[j], fsh[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = gn_apply_two<false>(h[j], ga[j], gb[j], fs[j], fsh[j]);
+              }
               *p = v;
             }
           }

@@ -22,4 +22,20 @@ __device__ __forceinline__ float gn_apply_one(float x, float ga, float gb, float
   return t;
 }
 
+// Two elements at once with packed conversions (same results as gn_apply_one: the fp16 product
+// t*fs is exact in fp32, so __hmul2's single rounding equals round_h(fp32 product); the add stays
+// an fp32 add + rounding like the reference's fp16 tensor add).
+template <bool FILM>
+__device__ __forceinline__ __half2 gn_apply_two(__half2 x, float2 ga, float2 gb, __half2 fs,
+                                                float2 fsh) {
+  const float2 xf = __half22float2(x);
+  __half2 t = __floats2half2_rn(xf.x * ga.x + gb.x, xf.y * ga.y + gb.y);
+  if (FILM) {
+    const float2 m = __half22float2(__hmul2(t, fs));
+    t = __floats2half2_rn(m.x + fsh.x, m.y + fsh.y);
+  }
+  const float2 tf = __half22float2(t);
+  return __floats2half2_rn(gnm_silu_fast(tf.x), gnm_silu_fast(tf.y));
+}
+
 }  // namespace pdr

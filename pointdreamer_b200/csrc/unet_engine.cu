@@ -180,9 +180,11 @@ class UnetEngine {
   int B_ = 0;
   size_t off_stats_[2] = {0, 0}, off_gnws_ = 0, off_e1_ = 0, off_emb_ = 0, off_emb16_ = 0;
   size_t off_partial_ = 0, partial_bytes_ = 0, partial_reserved_ = 0;
-  // GroupNorm + SiLU fused into the halo conv's transform warps; PDR_NO_FUSED_GN=1 (read at every
-  // plan) keeps the separate gn_apply pass - both paths produce the same bits
-  bool fuse_gn_ = true;
+  // GroupNorm + SiLU fused into the halo conv's transform warps: OPT-IN with PDR_FUSED_GN=1 (read
+  // at every plan).  Both paths produce the same bits, but the fused convs are 1.36-1.8x slower
+  // (the transform warps cannot keep up with the tensor core: ~7200 warp-instructions per chunk
+  // at IPC ~1.3), which costs more than the removed gn_apply pass saves
+  bool fuse_gn_ = false;
 
  public:
   size_t off_tcur_ = 0;  // float[B]: the timestep the captured graph reads
@@ -485,7 +487,7 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
   clear_plan();
   pl_ = Planner();
   dry_ = dry;
-  fuse_gn_ = getenv("PDR_NO_FUSED_GN") == nullptr;
+  fuse_gn_ = getenv("PDR_FUSED_GN") != nullptr;
   B_ = B;
   arena = (uint8_t*)workspace;
   arena_bytes = ws_bytes;

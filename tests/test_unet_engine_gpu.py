@@ -110,8 +110,8 @@ def test_engine_full_size_vs_oracle(cuda):
 
 
 def test_fused_groupnorm_equals_separate_pass_bitwise(cuda):
-    """GroupNorm+SiLU applied by the halo conv's transform warps (default) vs the separate gn_apply
-    pass (PDR_NO_FUSED_GN=1, read at plan time): same arithmetic per element, same accumulation
+    """GroupNorm+SiLU applied by the halo conv's transform warps (opt-in: PDR_FUSED_GN=1, read at
+    plan time) vs the separate gn_apply pass (default): same arithmetic per element, same accumulation
     order in the conv -> identical output bits, on a model with FiLM, skip convs and two-source
     (concatenated) inputs."""
     import os
@@ -125,15 +125,15 @@ def test_fused_groupnorm_equals_separate_pass_bitwise(cuda):
     x = torch.randn(3, 3, 64, 64, generator=g).to(cuda)
     t = torch.tensor([10.0, 500.0, 990.0], device=cuda)
     outs = []
-    for no_fuse in (False, True):
-        if no_fuse:
-            os.environ["PDR_NO_FUSED_GN"] = "1"
+    for fuse in (True, False):
+        if fuse:
+            os.environ["PDR_FUSED_GN"] = "1"
         else:
-            os.environ.pop("PDR_NO_FUSED_GN", None)
+            os.environ.pop("PDR_FUSED_GN", None)
         try:
             eng = UNetEngine(sd, cfg, device=cuda)
             outs.append(eng(x, t).clone())
         finally:
-            os.environ.pop("PDR_NO_FUSED_GN", None)
+            os.environ.pop("PDR_FUSED_GN", None)
     assert torch.isfinite(outs[0]).all() and outs[0].abs().max() > 0
     assert torch.equal(outs[0], outs[1])
