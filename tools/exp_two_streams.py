@@ -1,4 +1,5 @@
-"""Experiment: do two half-batch DDNM samplers on two CUDA streams (tensor-bound convs of one
+"""Experiment (result: no gain, 0.998x; the 4-engine variant HUNG the GPU box once - always run under
+`timeout`, and do not pass an argument > 2): do two half-batch DDNM samplers on two CUDA streams (tensor-bound convs of one
 overlapping the HBM-bound GroupNorm / attention of the other) beat one full-batch sampler?"""
 import sys, os, time, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
