@@ -900,13 +900,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           }
           mbar_wait(&a_full[as], aph);
           if (ch < chunks_main) {
+            // branch-free over the thread's rows: all loads first, 24 independent half2 chains,
+            // predicated stores (rows outside the image keep TMA's zeros; a row index past the
+            // tile only happens in the last step and stays inside the padded stage)
             uint8_t* base = smem + as * HALO_STAGE + toff;
+            uint4 v[NROWS];
+#pragma unroll
+            for (int i = 0; i < NROWS; ++i) v[i] = *(const uint4*)(base + i * RSTEP * 128);
 #pragma unroll
             for (int i = 0; i < NROWS; ++i) {
-              if (!((vmask >> i) & 1u)) continue;
-              uint4* p = (uint4*)(base + i * RSTEP * 128);
-              uint4 v = *p;
-              __half2* h = (__half2*)&v;
+              __half2* h = (__half2*)&v[i];
               if (film) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) h[j] = gn_apply_two<true>(h[j], ga[j], gb[j], fs[j], fsh[j]);
@@ -914,8 +917,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 4; ++j) h[j] = gn_apply_two<false>(h[j], ga[j], gb[j], fs[j], fsh[j]);
               }
-              *p = v;
             }
+#pragma unroll
+            for (int i = 0; i < NROWS; ++i)
+              if ((vmask >> i) & 1u) *(uint4*)(base + i * RSTEP * 128) = v[i];
           }
           fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's reads
           __syncwarp();
