@@ -40,6 +40,9 @@ unsigned long long pdr_launch_count(void);
  *   bias [Cout] fp32 or NULL; residual [B,H,W,Cout] fp16 or NULL; out [B,H,W,Cout] fp16
  *   bn: N tile, 64 / 128 / 256 (must divide Cout), 512 = 2-CTA kernel (cta_group::2, SM pairs share
  *   the weight tile; needs Cout % 256 == 0 and an even number of 128-pixel tiles), 0 = auto.
+ *   3x3 convs on maps with W % 8 == 0 and H % 16 == 0 run the halo kernel (all nine taps of a
+ *   64-channel chunk read one 10x18-pixel shared-memory tile); every variant accumulates K in the
+ *   same order, so the output bits do not depend on bn.
  *   C1, C2, Cout % 64 == 0. */
 int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias,
                 const void* residual, void* out, int B, int H, int W, int C1, int C2, int Cout,
