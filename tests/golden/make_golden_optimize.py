@@ -88,6 +88,15 @@ def main():
     out.update(atlas_out=atlas_out.detach().numpy(),
                images_s8=images.detach().numpy()[:, :, ::8, ::8].astype(np.float64),
                images_sum=np.float64(images.detach().double().sum().item()))
+    # ---- second case: optimize_from == 'naive' (no visibility mask), demo.py:221-223 ----
+    with ref_loader.quiet(), ref_loader.cuda_literals_to_cpu():
+        atlas_in = torch.from_numpy(atlas0.copy()).permute(2, 0, 1).flip(1)
+        atlas_nv, images_nv = ou.optimize_color(
+            atlas_in, torch.from_numpy(imgs), vertices, faces, uvs, mesh_tex_idx, cams, eye_t,
+            look_ats, up_dirs, uv_centers, uv_scales, padding, torch.from_numpy(scale_factors),
+            None, shrinked_per_view_per_pixel_visibility=None, iterations=4)
+    out.update(atlas_out_novis=atlas_nv.detach().numpy(),
+               images_sum_novis=np.float64(images_nv.detach().double().sum().item()))
     path = os.path.join(HERE, "optimize_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k: getattr(v, "shape", None) for k, v in out.items()})

@@ -136,3 +136,11 @@ def test_optimize_color_deterministic(cuda, golden):
     a1, _ = _run_cuda(cuda, golden, 12, 256, want_images=False)
     a2, _ = _run_cuda(cuda, golden, 12, 256, want_images=False)
     assert torch.equal(a1, a2)
+
+
+def test_optimize_color_without_visibility_vs_reference_fixture(cuda, golden):
+    """optimize_from == 'naive' (no visibility mask), 4 iterations at the reference's 1024^2."""
+    atlas, _ = _run_cuda(cuda, golden, 4, 1024, vis=False, want_images=False)
+    err = np.abs(atlas.cpu().numpy() - golden["atlas_out_novis"])
+    print("optimize_color (no vis) vs reference fixture: max abs", err.max())
+    assert err.max() < 1e-3

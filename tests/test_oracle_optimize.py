@@ -60,3 +60,18 @@ def test_optimize_color_matches_reference(golden):
     assert abs(images.sum() - golden["images_sum"]) <= 1e-9 * abs(golden["images_sum"])
     # the optimiser did move the covered texels
     assert np.abs(atlas[0] - atlas_in).max() > 0.05
+
+
+def test_optimize_color_without_visibility_matches_reference(golden):
+    """optimize_from == 'naive': no shrinked-visibility mask (demo.py:221-223), 4 iterations."""
+    sc, imgs, atlas0, vis, scale_factors = inputs()
+    xa = sc["xatlas_dict"]
+    cams, _, _, _ = ocam.create_cameras(CFG["view_num"], 1.6, CFG["cam_res"])
+    uv_map, mask = oopt.view_uv_maps([c.params for c in cams], sc["vertices"], sc["faces"],
+                                     xa["uvs"], xa["mesh_tex_idx"], golden["uv_centers"],
+                                     golden["uv_scales"], CFG["padding"], scale_factors, 1024)
+    atlas_in = np.ascontiguousarray(atlas0.transpose(2, 0, 1)[:, ::-1])
+    atlas, images = oopt.optimize_color(atlas_in, imgs, uv_map, mask, shrinked_vis=None,
+                                        iterations=4, res=1024)
+    assert np.abs(atlas - golden["atlas_out_novis"]).max() == 0.0
+    assert abs(images.sum() - golden["images_sum_novis"]) <= 1e-9 * abs(golden["images_sum_novis"])
