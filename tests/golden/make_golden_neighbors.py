@@ -38,9 +38,9 @@ def inputs(cfg=CFG, unseen_below=-0.12):
     return sc, atlas.astype(np.float32), painted, ids
 
 
-def main():
+def run_reference(unseen_below):
     un = ref_loader.load("pointdreamer.unproject")
-    sc, atlas, painted, ids = inputs()
+    sc, atlas, painted, ids = inputs(unseen_below=unseen_below)
     xa = sc["xatlas_dict"]
     with ref_loader.quiet():
         out = un.paint_invisible_areas_by_neighbors(
@@ -48,9 +48,16 @@ def main():
             torch.from_numpy(xa["uvs"]), torch.from_numpy(xa["mesh_tex_idx"]),
             torch.from_numpy(ids), torch.from_numpy(atlas.copy()),
             torch.from_numpy(painted.copy()), use_atlas=True)
+    return out.numpy().astype(np.float32), len(ids)
+
+
+def main():
+    out, n = run_reference(-0.12)
+    out2, n2 = run_reference(0.05)   # a larger never-seen region: more colouring rounds
     path = os.path.join(HERE, "neighbors_small.npz")
-    np.savez_compressed(path, atlas_out=out.numpy().astype(np.float32), n_to_inpaint=np.int64(len(ids)))
-    print("wrote", path, out.shape, out.dtype, "faces to inpaint:", len(ids))
+    np.savez_compressed(path, atlas_out=out, n_to_inpaint=np.int64(n), atlas_out_b=out2,
+                        n_to_inpaint_b=np.int64(n2))
+    print("wrote", path, out.shape, "faces to inpaint:", n, n2)
 
 
 if __name__ == "__main__":

@@ -75,3 +75,17 @@ def test_subdivide_with_no_faces_selected_is_identity():
     vo, fo, uvo, fuvo = onb.subdivide_with_uv(sc["vertices"], sc["faces"], xa["mesh_tex_idx"],
                                               xa["uvs"], face_index=none)
     assert np.array_equal(fo, sc["faces"]) and np.array_equal(uvo, xa["uvs"])
+
+
+def test_paint_invisible_areas_by_neighbors_second_case_matches_reference():
+    """A larger never-seen region (surface below y = 0.05): more faces, more colouring rounds."""
+    sc, atlas, painted, ids = inputs(unseen_below=0.05)
+    xa = sc["xatlas_dict"]
+    g = np.load(os.path.join(HERE, "golden", "neighbors_small.npz"))
+    out, tie, rounds = onb.paint_invisible_areas_by_neighbors(
+        sc["vertices"], sc["faces"], xa["uvs"], xa["mesh_tex_idx"], ids, atlas, painted)
+    assert int(g["n_to_inpaint_b"]) == len(ids) and rounds >= 2
+    err = np.abs(out - g["atlas_out_b"])
+    assert np.array_equal(out[painted], atlas[painted])
+    assert err[~tie].max() < 1e-5
+    assert (err.max(-1) > 1e-5).sum() <= tie.sum()
