@@ -230,7 +230,7 @@ def main():
     scene_host["xatlas_dict"] = {k: pin(v) for k, v in scene_np["xatlas_dict"].items()}
     scene_dev = {k: v.to(dev) for k, v in scene_host.items() if k != "xatlas_dict"}
     xa_dev = {k: v.to(dev) for k, v in scene_host["xatlas_dict"].items()}
-    inpainter = Inpainter(dev, seed=42, offset=0)
+    inpainter = Inpainter(dev, seed=42, offset=0, allow_random_weights=True)
     cam_info = demo.prepare_cameras(cfg, dev)
     keys = {k: cfg[k] for k in demo.PATH_CONFIG_KEYS}
 

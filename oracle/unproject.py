@@ -71,10 +71,16 @@ def shrink_visibility(per_pixel_mask, vis, kernel_sizes):
 
 
 def softmax_rows(s):
-    """torch.softmax(x, 1) in fp32: exp(x - max) / sum."""
+    """torch.softmax(x, 1) in fp32: exp(x - max) / sum.  Canonical arithmetic (the library exp and
+    the reduction order of torch's softmax are unpinned): exp evaluated in float64 and rounded
+    once to fp32 (== the correctly rounded fp32 exp), the sum accumulated in fp32 in view order,
+    one IEEE fp32 division - exactly what unproj_select_kernel does."""
     m = s.max(1, keepdims=True)
-    e = np.exp((s - m).astype(F32)).astype(F32)
-    return (e / e.sum(1, keepdims=True, dtype=F32)).astype(F32)
+    e = np.exp((s - m).astype(F32).astype(np.float64)).astype(F32)
+    tot = np.zeros((s.shape[0], 1), dtype=F32)
+    for v in range(s.shape[1]):
+        tot = (tot + e[:, v:v + 1]).astype(F32)
+    return (e / tot).astype(F32)
 
 
 def unproject(inpainted_images, f_normals, view_img_res, cam_params, cam_res, base_dirs, gb_pos,

@@ -54,8 +54,9 @@ __global__ void unproj_visibility_kernel(const float* __restrict__ cams,
     for (int v = 0; v < V; ++v) {
       float nx, ny, nz, u_ns, v_ns, u_s, v_s;
       cam_transform(sc + v * CAM_PARAM_FLOATS, x, y, z, nx, ny, nz);
-      texel_uv(nx, ny, centers[2 * v], centers[2 * v + 1], scales[v], pad_mul, rescale, 1.0f,
-               u_ns, v_ns, u_s, v_s);
+      // rescale == 0 (unproject.py:262-264): the crop arrays may be NULL and are not read
+      texel_uv(nx, ny, rescale ? centers[2 * v] : 0.f, rescale ? centers[2 * v + 1] : 0.f,
+               rescale ? scales[v] : 2.f, pad_mul, rescale, 1.0f, u_ns, v_ns, u_s, v_s);
       const float fc = (float)cam_res;
       const long long col = (long long)clipf(u_ns * fc, 0.f, (float)(cam_res - 1));
       const long long row = (long long)clipf(v_ns * fc, 0.f, (float)(cam_res - 1));
@@ -165,7 +166,9 @@ __global__ void unproj_select_kernel(const float* __restrict__ cams,
     }
     float sum = 0.f;
     for (int v = 0; v < V; ++v) {
-      sim[v] = expf(sim[v] - mx);
+      // correctly rounded fp32 exp (float64 evaluation, one rounding): the canonical rule of
+      // oracle/unproject.py:softmax_rows, independent of the library's expf
+      sim[v] = (float)exp((double)(sim[v] - mx));
       sum += sim[v];
     }
     float best = -INFINITY;
@@ -180,8 +183,9 @@ __global__ void unproj_select_kernel(const float* __restrict__ cams,
       const float x = gb_pos[3 * i], y = gb_pos[3 * i + 1], z = gb_pos[3 * i + 2];
       float nx, ny, nz, u_ns, v_ns, u_s, v_s;
       cam_transform(sc + vid * CAM_PARAM_FLOATS, x, y, z, nx, ny, nz);
-      texel_uv(nx, ny, centers[2 * vid], centers[2 * vid + 1], scales[vid], pad_mul, rescale,
-               scale_factors[vid], u_ns, v_ns, u_s, v_s);
+      texel_uv(nx, ny, rescale ? centers[2 * vid] : 0.f, rescale ? centers[2 * vid + 1] : 0.f,
+               rescale ? scales[vid] : 2.f, pad_mul, rescale, rescale ? scale_factors[vid] : 1.f,
+               u_ns, v_ns, u_s, v_s);
       const float fr = (float)res;
       const long long col = (long long)clipf(u_s * fr, 0.f, (float)(res - 1));
       const long long row = (long long)clipf(v_s * fr, 0.f, (float)(res - 1));

@@ -81,23 +81,33 @@ def step_table(cfg):
 class Inpainter:
     """`Inpainter(device).inpaint(masked_imgs, masks)` like the reference, plus `inpaint_batch`.
 
-    state_dict: weights under the reference's parameter names; default: load
-    `ckpt_path` (models/DDNM/256x256_diffusion_uncond.pt) when it exists, otherwise seeded
-    random-init weights of the same architecture (no network for the checkpoint here).
+    state_dict: weights under the reference's parameter names; default: load `ckpt_path`
+    (models/DDNM/256x256_diffusion_uncond.pt).  A missing checkpoint is an error, as in the
+    reference (diffusion.py:435-457 downloads or fails); seeded random-init weights of the same
+    architecture are used only on the explicit opt-in `allow_random_weights=True` (benchmarks
+    and tests: there is no network for the checkpoint here).  `synthetic_weights` tells which.
     seed / offset: position of torch's Philox stream at DDNM entry (the reference uses the
     global CUDA generator, effectively kiui.seed_everything(42), demo.py:34)."""
 
     def __init__(self, device, state_dict=None, model_config=None, ddnm_config=None, seed=42,
-                 offset=0, ckpt_path='models/DDNM/256x256_diffusion_uncond.pt'):
+                 offset=0, ckpt_path='models/DDNM/256x256_diffusion_uncond.pt',
+                 allow_random_weights=False):
         self.device = torch.device(device)
         self.model_config = dict(DEFAULT_MODEL_CONFIG if model_config is None else model_config)
         self.ddnm_config = dict(DEFAULT_DDNM_CONFIG if ddnm_config is None else ddnm_config)
+        self.synthetic_weights = False
         if state_dict is None:
             if os.path.exists(ckpt_path):
                 state_dict = torch.load(ckpt_path, map_location="cpu")
-            else:
+            elif allow_random_weights:
                 state_dict = random_state_dict(self.model_config, seed=1234, device=self.device)
                 self.synthetic_weights = True
+            else:
+                raise FileNotFoundError(
+                    f"DDNM checkpoint not found at {os.path.abspath(ckpt_path)!r} (the reference "
+                    "loads models/DDNM/256x256_diffusion_uncond.pt, diffusion.py:435-457); pass "
+                    "ckpt_path=, state_dict=, or allow_random_weights=True for seeded random-init "
+                    "weights of the same architecture")
         self.model = UNetEngine(state_dict, self.model_config, device=self.device)
         self.ts, self.coefs = step_table(self.ddnm_config)
         self.seed = int(seed)

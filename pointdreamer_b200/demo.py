@@ -48,6 +48,58 @@ def prepare_cameras(cfg, device):
                 cam_RTs=None, cam_K=None)
 
 
+def _num_texels(xatlas_dict):
+    """mask.sum() of an atlas, computed once per xatlas_dict and kept in it (the chart mask is
+    static per mesh, demo.py:430-448), so repeated colorize calls do not synchronise the host."""
+    n = xatlas_dict.get('_pdr_num_texels')
+    if n is None:
+        n = _un.count_texels(xatlas_dict['mask'])
+        xatlas_dict['_pdr_num_texels'] = n
+    return n
+
+
+def _after_path(atlas_img, atlas_painted_mask, shrinked_vis, inpainted_images, vertices, faces,
+                uvs, mesh_tex_idx, mask, per_atlas_pixel_face_id, cams, eye_positions, up_dirs,
+                uv_centers, uv_scales, padding, inpaint_scale_factors, glctx, complete_unseen_by,
+                optimize_from, neighbor_fill=None, optimize_color=None, _mark=lambda name: None):
+    """demo.py:180-246, what the reference runs AFTER project -> inpaint -> unproject inside
+    colorize_one_mesh: unseen-texel completion ("next" row N2) and optimize_color (N1)."""
+    if complete_unseen_by == 'unproject':
+        atlas_img = _un.dilate_atlas(atlas_img, mask)
+    elif complete_unseen_by == 'neighbor':
+        if neighbor_fill is None:
+            neighbor_fill = _un.paint_invisible_areas_by_neighbors
+        to_inpaint_face_id = per_atlas_pixel_face_id[0][torch.logical_not(atlas_painted_mask)].unique()
+        to_inpaint_face_id = to_inpaint_face_id[to_inpaint_face_id > -1]
+        atlas_img = neighbor_fill(vertices, faces, uvs, mesh_tex_idx, to_inpaint_face_id,
+                                  atlas_img, atlas_painted_mask, use_atlas=True)
+    elif complete_unseen_by == 'optimize':
+        raise NotImplementedError("complete_unseen_by='optimize' (TextureField) is out of scope")
+    _mark("complete_unseen")
+    # ---- demo.py:211-233: refine the atlas against the inpainted views ("next" row N1)
+    if optimize_from is not None and optimize_from != 'None':
+        if optimize_color is not None:  # caller-supplied replacement
+            atlas_img = optimize_color(atlas_img, inpainted_images, shrinked_vis)
+        else:
+            atlas_in = atlas_img.permute(2, 0, 1).flip(1)  # [3,R,R]
+            if optimize_from == 'scratch':
+                init_atlas, vis = None, None
+            elif optimize_from == 'naive':
+                init_atlas, vis = atlas_in, None
+            elif optimize_from == 'ours':
+                init_atlas, vis = atlas_in, shrinked_vis
+            else:
+                raise ValueError(f"optimize_from={optimize_from!r}")
+            atlas_opt, _ = _ou.optimize_color(
+                init_atlas, inpainted_images, vertices, faces, uvs, mesh_tex_idx, cams,
+                eye_positions, None, up_dirs, uv_centers, uv_scales, padding,
+                inpaint_scale_factors, glctx, shrinked_per_view_per_pixel_visibility=vis,
+                return_images=False)
+            atlas_img = atlas_opt[0].flip(1).permute(1, 2, 0)  # [R,R,3]
+    _mark("optimize_color")
+    return atlas_img
+
+
 def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, camera_info,
                       view_num, res, cam_res, refine_res, device, save_img_path,
                       point_validation_by_o3d, refine_point_validation_by_remove_abnormal_depth,
@@ -117,43 +169,14 @@ def colorize_one_mesh(coords, colors, vertices, faces, f_normals, xatlas_dict, c
             inpainted_images, vertices, f_normals, res, cams, cam_res, base_dirs, gb_pos, mask,
             per_atlas_pixel_face_id, uv_centers, uv_scales, padding, inpaint_scale_factors,
             mesh_normalized_depths, edge_dilate_kernels, save_img_path,
-            complete_unseen_by_projection)
+            complete_unseen_by_projection, num_texels=_num_texels(xatlas_dict))
 
         _mark("unproject")
-        # ---- after the path (demo.py:180-246): "next" rows
-        if complete_unseen_by == 'unproject':
-            atlas_img = _un.dilate_atlas(atlas_img, mask)
-        elif complete_unseen_by == 'neighbor':
-            if neighbor_fill is None:
-                neighbor_fill = _un.paint_invisible_areas_by_neighbors
-            to_inpaint_face_id = per_atlas_pixel_face_id[0][torch.logical_not(atlas_painted_mask)].unique()
-            to_inpaint_face_id = to_inpaint_face_id[to_inpaint_face_id > -1]
-            atlas_img = neighbor_fill(vertices, faces, uvs, mesh_tex_idx, to_inpaint_face_id,
-                                      atlas_img, atlas_painted_mask, use_atlas=True)
-        elif complete_unseen_by == 'optimize':
-            raise NotImplementedError("complete_unseen_by='optimize' (TextureField) is out of scope")
-        _mark("complete_unseen")
-        # ---- demo.py:211-233: refine the atlas against the inpainted views ("next" row N1)
-        if optimize_from is not None and optimize_from != 'None':
-            if optimize_color is not None:  # caller-supplied replacement
-                atlas_img = optimize_color(atlas_img, inpainted_images, shrinked_vis)
-            else:
-                atlas_in = atlas_img.permute(2, 0, 1).flip(1)  # [3,R,R]
-                if optimize_from == 'scratch':
-                    init_atlas, vis = None, None
-                elif optimize_from == 'naive':
-                    init_atlas, vis = atlas_in, None
-                elif optimize_from == 'ours':
-                    init_atlas, vis = atlas_in, shrinked_vis
-                else:
-                    raise ValueError(f"optimize_from={optimize_from!r}")
-                atlas_opt, _ = _ou.optimize_color(
-                    init_atlas, inpainted_images, vertices, faces, uvs, mesh_tex_idx, cams,
-                    eye_positions, None, camera_info.get('up_dirs'), uv_centers, uv_scales,
-                    padding, inpaint_scale_factors, glctx,
-                    shrinked_per_view_per_pixel_visibility=vis, return_images=False)
-                atlas_img = atlas_opt[0].flip(1).permute(1, 2, 0)  # [R,R,3]
-        _mark("optimize_color")
+        atlas_img = _after_path(
+            atlas_img, atlas_painted_mask, shrinked_vis, inpainted_images, vertices, faces, uvs,
+            mesh_tex_idx, mask, per_atlas_pixel_face_id, cams, eye_positions,
+            camera_info.get('up_dirs'), uv_centers, uv_scales, padding, inpaint_scale_factors,
+            glctx, complete_unseen_by, optimize_from, neighbor_fill, optimize_color, _mark)
     return vertices, uvs, faces, mesh_tex_idx, atlas_img, mask
 
 
@@ -162,7 +185,8 @@ def colorize_batch(scenes, camera_info, cfg, inpainter, device):
     shape; all S*V diffusion chains run as ONE U-Net batch (chain s*V+v keeps the noise-stream slot
     the reference's serial loop over shapes and views would give it).  `scenes`: list of dicts with
     device tensors xyz, rgb, vertices, faces, f_normals, xatlas_dict.  Returns a list of atlases.
-    Only the path itself (complete_unseen_by in {None,'unproject'}, optimize_from None)."""
+    The post-path steps cfg asks for (complete_unseen_by, optimize_from) run per shape exactly as
+    in colorize_one_mesh, so the result equals shape-by-shape calls."""
     keys = {k: cfg[k] for k in PATH_CONFIG_KEYS}
     V, res, cam_res = keys["view_num"], keys["res"], keys["cam_res"]
     if keys["texture_gen_method"] != "DDNM_inpaint":
@@ -196,15 +220,19 @@ def colorize_batch(scenes, camera_info, cfg, inpainter, device):
         atlases = []
         for i, (sc, st) in enumerate(zip(scenes, staged)):
             xa = sc["xatlas_dict"]
-            atlas = _un.unproject(inpainted[i * V:(i + 1) * V], sc["vertices"], sc["f_normals"], res,
-                                  cams, cam_res, camera_info['base_dirs'], xa["gb_pos"], xa["mask"],
-                                  xa["per_atlas_pixel_face_id"], st["uv_centers"], st["uv_scales"],
-                                  st["padding"], st["scales"], st["depths"],
-                                  keys["edge_dilate_kernels"], None,
-                                  keys["complete_unseen_by"] == 'unproject')[0]
-            if keys["complete_unseen_by"] == 'unproject':
-                atlas = _un.dilate_atlas(atlas, xa["mask"])
-            atlases.append(atlas)
+            views = inpainted[i * V:(i + 1) * V]
+            atlas, shr, _, _, _, painted = _un.unproject(
+                views, sc["vertices"], sc["f_normals"], res, cams, cam_res,
+                camera_info['base_dirs'], xa["gb_pos"], xa["mask"], xa["per_atlas_pixel_face_id"],
+                st["uv_centers"], st["uv_scales"], st["padding"], st["scales"], st["depths"],
+                keys["edge_dilate_kernels"], None, keys["complete_unseen_by"] == 'unproject',
+                num_texels=_num_texels(xa))
+            atlases.append(_after_path(
+                atlas, painted, shr, views, sc["vertices"], sc["faces"], xa.get("uvs"),
+                xa.get("mesh_tex_idx"), xa["mask"], xa["per_atlas_pixel_face_id"], cams,
+                camera_info['eye_positions'], camera_info.get('up_dirs'), st["uv_centers"],
+                st["uv_scales"], st["padding"], st["scales"], None, keys["complete_unseen_by"],
+                keys["optimize_from"]))
     return atlases
 
 
@@ -218,6 +246,7 @@ def colorize_from_host(scene, camera_info, cfg, inpainter, device):
     h2d = sum(t.numel() * t.element_size() for t in host)
     d = [t.to(device, non_blocking=True) for t in host]
     xad = dict(uvs=d[5], mesh_tex_idx=d[6], gb_pos=d[7], mask=d[8], per_atlas_pixel_face_id=d[9])
+    xad['_pdr_num_texels'] = int(xa["mask"].sum())  # counted on the host copy: no device sync
     keys = {k: cfg[k] for k in PATH_CONFIG_KEYS}
     out = colorize_one_mesh(d[0], d[1], d[2], d[3], d[4], xad, camera_info, device=device,
                             save_img_path=None, inpainter=inpainter, glctx=None, logger=None, **keys)
@@ -285,7 +314,7 @@ def recon_one_textured_mesh(cfg, inpainter, camera_info, pc_file, name, device, 
             None, vertices, faces, resolution=R, parametrization=par)
         xatlas_dict = {'uvs': uvs, 'mesh_tex_idx': mesh_tex_idx, 'gb_pos': gb_pos, 'mask': mask,
                        'per_atlas_pixel_face_id': face_id}
-        torch.save(xatlas_dict, xatlas_save_file)
+        torch.save({k: v for k, v in xatlas_dict.items() if torch.is_tensor(v)}, xatlas_save_file)
 
     keys = {k: cfg[k] for k in PATH_CONFIG_KEYS}
     vertices, uvs, faces, mesh_tex_idx, atlas_img, mask = colorize_one_mesh(

@@ -46,27 +46,92 @@ def load_inpainted_pngs(save_path, view_num, res):
     return out
 
 
+_PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2",
+              "int16": "i2", "ushort": "u2", "uint16": "u2", "int": "i4", "int32": "i4",
+              "uint": "u4", "uint32": "u4", "float": "f4", "float32": "f4", "double": "f8",
+              "float64": "f8"}
+
+
 def read_ply_xyzrgb(path):
-    """utils/other_utils.py:155-162 without plyfile: the reference's demo clouds are binary
-    little-endian PLY with `x y z` float32 and `red green blue` uchar per vertex (15 B/vertex).
-    Returns (xyz float32 [N,3], rgb uint8 [N,3])."""
+    """utils/other_utils.py:155-162 without plyfile.  The reference's demo clouds are binary
+    little-endian PLY with `x y z` float32 and `red green blue` uchar per vertex (15 B/vertex);
+    like plyfile this reader also accepts big-endian and ASCII bodies, CRLF headers, extra
+    vertex properties, and further elements (e.g. `face` with a `property list`) around the
+    vertex element.  Returns (xyz float32 [N,3], rgb uint8 [N,3])."""
     with open(path, "rb") as f:
-        header = b""
-        while not header.endswith(b"end_header\n"):
+        lines = []
+        while True:
             line = f.readline()
             if not line:
                 raise ValueError(f"{path}: no end_header")
-            header += line
-        text = header.decode("ascii", "replace")
-        if "binary_little_endian" not in text:
-            raise NotImplementedError("only binary_little_endian PLY clouds are supported")
-        n = int([l for l in text.splitlines() if l.startswith("element vertex")][0].split()[-1])
-        props = [l.split()[1:] for l in text.splitlines() if l.startswith("property")]
-        dt = []
-        for typ, name in props:
-            dt.append((name, {"float": "<f4", "float32": "<f4", "uchar": "u1", "uint8": "u1",
-                              "double": "<f8", "int": "<i4"}[typ]))
-        data = np.frombuffer(f.read(n * np.dtype(dt).itemsize), dtype=np.dtype(dt), count=n)
+            txt = line.decode("ascii", "replace").strip()  # strips \r\n as well as \n
+            if txt == "end_header":
+                break
+            lines.append(txt)
+        if not lines or lines[0] != "ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt = None
+        elements = []  # [name, count, [(kind, ...)]] in file order
+        for l in lines[1:]:
+            tok = l.split()
+            if not tok or tok[0] in ("comment", "obj_info"):
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                elements.append([tok[1], int(tok[2]), []])
+            elif tok[0] == "property":
+                if not elements:
+                    raise ValueError(f"{path}: property before any element")
+                if tok[1] == "list":
+                    if tok[2] not in _PLY_TYPES or tok[3] not in _PLY_TYPES:
+                        raise ValueError(f"{path}: unsupported PLY list types {tok[2:4]}")
+                    elements[-1][2].append(("list", tok[2], tok[3], tok[4]))
+                else:
+                    if tok[1] not in _PLY_TYPES:
+                        raise ValueError(f"{path}: unsupported PLY property type {tok[1]!r}")
+                    elements[-1][2].append(("scalar", tok[1], tok[2]))
+        if fmt not in ("binary_little_endian", "binary_big_endian", "ascii"):
+            raise ValueError(f"{path}: unsupported PLY format {fmt!r}")
+        end = ">" if fmt == "binary_big_endian" else "<"
+        data = None
+        for name, count, props in elements:
+            has_list = any(p[0] == "list" for p in props)
+            if name == "vertex":
+                if has_list:
+                    raise ValueError(f"{path}: list property on the vertex element")
+                dt = np.dtype([(p[2], end + _PLY_TYPES[p[1]]) for p in props])
+                if fmt == "ascii":
+                    rows = [f.readline().split() for _ in range(count)]
+                    data = np.zeros(count, dtype=dt)
+                    for j, p in enumerate(props):
+                        data[p[2]] = np.asarray([r[j] for r in rows], dtype=np.float64)
+                else:
+                    raw = f.read(count * dt.itemsize)
+                    if len(raw) != count * dt.itemsize:
+                        raise ValueError(f"{path}: truncated vertex data")
+                    data = np.frombuffer(raw, dtype=dt, count=count)
+                break
+            # an element stored BEFORE the vertices has to be skipped
+            if fmt == "ascii":
+                for _ in range(count):
+                    f.readline()
+            elif not has_list:
+                f.seek(count * sum(np.dtype(_PLY_TYPES[p[1]]).itemsize for p in props), 1)
+            else:
+                for _ in range(count):
+                    for p in props:
+                        if p[0] == "scalar":
+                            f.seek(np.dtype(_PLY_TYPES[p[1]]).itemsize, 1)
+                        else:
+                            cdt = np.dtype(end + _PLY_TYPES[p[1]])
+                            k = int(np.frombuffer(f.read(cdt.itemsize), dtype=cdt)[0])
+                            f.seek(k * np.dtype(_PLY_TYPES[p[2]]).itemsize, 1)
+        if data is None:
+            raise ValueError(f"{path}: no vertex element")
+    for k in ("x", "y", "z", "red", "green", "blue"):
+        if k not in data.dtype.names:
+            raise ValueError(f"{path}: vertex property {k!r} missing")
     xyz = np.stack([data["x"], data["y"], data["z"]], -1).astype(np.float32)
     rgb = np.stack([data["red"], data["green"], data["blue"]], -1).astype(np.uint8)
     return xyz, rgb

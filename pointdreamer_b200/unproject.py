@@ -19,8 +19,10 @@ def _per_view(x, V, n, dev):
 def unproject(inpainted_images, vertices, f_normals, view_img_res, cams, cam_res, base_dirs,
               gb_pos, mask, per_atlas_pixel_face_id, uv_centers, uv_scales, padding,
               inpaint_scale_factors, mesh_normalized_depths, edge_dilate_kernels, save_img_path,
-              complete_unseen_by_projection=False):
+              complete_unseen_by_projection=False, num_texels=None):
     """unproject.py:201-425.  `save_img_path` (debug PNG triptychs, 459-474) is ignored.
+    num_texels: P = mask.sum() when the caller already knows it (the chart mask is static per
+    xatlas_dict; `count_texels` computes it once) - then the call has no host synchronisation.
 
     Returns (atlas_img[R,R,3] f32, shrinked_vis[V,R,R] bool, point_view_ids[P] int64,
              points_atlas_pixel_coord[P,2] int64, points[P,3] f32, atlas_painted_mask[R,R] bool).
@@ -42,11 +44,7 @@ def unproject(inpainted_images, vertices, f_normals, view_img_res, cams, cam_res
     karr = (ctypes.c_int * n_levels)(*kernels)
 
     lib = _lib.load()
-    ws_counter = torch.zeros(1, dtype=torch.int32, device=dev)
-    count = ctypes.c_int(0)
-    _lib.call("pdr_mask_count", mask_u8, ctypes.c_size_t(R * R), ws_counter,
-              ctypes.byref(count))
-    P = count.value
+    P = int(num_texels) if num_texels is not None else count_texels(mask)
 
     lib.pdr_unproject_workspace_bytes.restype = ctypes.c_size_t
     ws = torch.empty(lib.pdr_unproject_workspace_bytes(R, n_levels), dtype=torch.uint8, device=dev)
@@ -73,6 +71,17 @@ def unproject(inpainted_images, vertices, f_normals, view_img_res, cams, cam_res
               shr, view_ids, coords, points,
               painted)
     return atlas, shr.bool(), view_ids, coords, points, painted.bool()
+
+
+def count_texels(mask):
+    """P = number of chart texels of the atlas mask [1,R,R,1] (one device reduction + one 4-byte
+    read back; the only host synchronisation of the UNPROJECT stage, done once per atlas)."""
+    mask_u8 = _u8(mask[0, :, :, 0]).contiguous()
+    ws_counter = torch.zeros(1, dtype=torch.int32, device=mask.device)
+    count = ctypes.c_int(0)
+    _lib.call("pdr_mask_count", mask_u8, ctypes.c_size_t(mask_u8.numel()), ws_counter,
+              ctypes.byref(count))
+    return count.value
 
 
 def dilate_atlas(atlas_img, mask):

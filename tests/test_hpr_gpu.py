@@ -18,7 +18,7 @@ def test_hpr_vs_reference_golden(cuda, name):
     ref = g["point_validation_o3d"]
     mism = int((vis != ref).sum())
     print(f"case {name}: visible {int(ref.sum())}/{ref.size}, mismatches {mism}")
-    assert mism <= max(1, int(2e-4 * ref.size))
+    assert mism == 0
 
 
 def test_hpr_full_size_vs_oracle(cuda):
@@ -38,4 +38,4 @@ def test_hpr_full_size_vs_oracle(cuda):
     ref = ohpr.point_validation_by_o3d(xyz, eyes, 100)
     mism = int((vis != ref).sum())
     print(f"30k x 8 views: visible {int(ref.sum())}, mismatches {mism}, {e0.elapsed_time(e1):.2f} ms")
-    assert mism <= int(2e-4 * ref.size)
+    assert mism == 0

@@ -61,3 +61,63 @@ def test_load_config_and_keys(tmp_path):
     cfg.update(demo.load_config(str(y)))
     assert cfg["view_num"] == 4 and cfg["texture_gen_method"] == "nearest"
     assert all(k in cfg for k in demo.PATH_CONFIG_KEYS)
+
+
+def test_ply_reader_accepts_what_plyfile_accepts(tmp_path):
+    """CRLF header, an element before the vertices, a face element with a list property, extra
+    vertex properties, big-endian and ASCII bodies (the reference reads clouds with plyfile)."""
+    import struct
+    xyz = np.array([[0.5, -1.25, 2.0], [3.0, 4.0, -5.5]], dtype=np.float32)
+    rgb = np.array([[1, 2, 3], [250, 128, 0]], dtype=np.uint8)
+
+    def write(path, fmt, nl):
+        end = ">" if fmt == "binary_big_endian" else "<"
+        hdr = ["ply", f"format {fmt} 1.0", "comment made by a test", "element camera 1",
+               "property float fx", "property list uchar int ids", "element vertex 2",
+               "property float x", "property float y", "property float z", "property float nx",
+               "property uchar red", "property uchar green", "property uchar blue",
+               "element face 1", "property list uchar int vertex_indices", "end_header"]
+        with open(path, "wb") as f:
+            f.write((nl.join(hdr) + nl).encode())
+            if fmt == "ascii":
+                f.write(b"1.5 2 7 8\n")
+                for p, c in zip(xyz, rgb):
+                    f.write(("%r %r %r 0.0 %d %d %d\n" % (float(p[0]), float(p[1]), float(p[2]),
+                                                          c[0], c[1], c[2])).encode())
+                f.write(b"3 0 1 0\n")
+            else:
+                f.write(struct.pack(end + "fBii", 1.5, 2, 7, 8))
+                for p, c in zip(xyz, rgb):
+                    f.write(struct.pack(end + "ffffBBB", p[0], p[1], p[2], 0.0, *[int(v) for v in c]))
+                f.write(struct.pack(end + "Biii", 3, 0, 1, 0))
+
+    for fmt, nl in [("binary_little_endian", "\n"), ("binary_little_endian", "\r\n"),
+                    ("binary_big_endian", "\n"), ("ascii", "\n")]:
+        p = str(tmp_path / f"{fmt}_{len(nl)}.ply")
+        write(p, fmt, nl)
+        x2, c2 = io_utils.read_ply_xyzrgb(p)
+        assert np.array_equal(x2, xyz) and np.array_equal(c2, rgb), (fmt, nl)
+
+
+def test_ply_reader_errors(tmp_path):
+    import pytest
+    p = str(tmp_path / "bad.ply")
+    open(p, "wb").write(b"ply\nformat binary_little_endian 1.0\nelement vertex 1\nproperty float x\n")
+    with pytest.raises(ValueError, match="end_header"):
+        io_utils.read_ply_xyzrgb(p)
+    open(p, "wb").write(b"ply\nformat binary_little_endian 1.0\nelement vertex 1\n"
+                        b"property quaternion x\nend_header\n")
+    with pytest.raises(ValueError, match="unsupported PLY property type"):
+        io_utils.read_ply_xyzrgb(p)
+    open(p, "wb").write(b"ply\nformat binary_little_endian 1.0\nelement vertex 1\n"
+                        b"property float x\nproperty float y\nproperty float z\nend_header\n" + b"\0" * 12)
+    with pytest.raises(ValueError, match="'red' missing"):
+        io_utils.read_ply_xyzrgb(p)
+
+
+def test_reference_demo_cloud_fixture():
+    """tests/golden/clock.ply is the reference's dataset/demo_data/clock.ply (BASELINE configs[0])."""
+    import os
+    from golden_util import GOLDEN_DIR
+    xyz, rgb = io_utils.read_ply_xyzrgb(os.path.join(GOLDEN_DIR, "clock.ply"))
+    assert xyz.shape == (30000, 3) and rgb.shape == (30000, 3) and rgb.dtype == np.uint8

@@ -29,7 +29,7 @@ sc = synthetic.make_scene(30000, seed=0)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 xyz, rgb, vertices, faces = t(sc["xyz"]), t(sc["rgb"]), t(sc["vertices"]), t(sc["faces"])
 cam = demo.prepare_cameras(cfg, dev)
-inp = Inpainter(dev, ddnm_config=dict(DEFAULT_DDNM_CONFIG, T_sampling=T), seed=42, offset=0)
+inp = Inpainter(dev, ddnm_config=dict(DEFAULT_DDNM_CONFIG, T_sampling=T), seed=42, offset=0, allow_random_weights=True)
 (hm, _, depths, _, uvc, uvs, pad, puv, pdep) = ou.get_rendered_hard_mask_and_face_idx_batch(
     cam["cams"], vertices, faces, xyz)
 hm = ou.resize_hard_masks(hm, res)
