@@ -1,14 +1,21 @@
 """bench.py — shapes/s of the project -> DDNM-inpaint -> unproject hot path on B200.
 
   python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank/GPU)
-  python bench.py --impl reference ...                   (CPU oracle arm, rank 0 only)
+  python bench.py --config {0,1,2,3,4}                   (BASELINE.json configs[i]; default 1)
+  python bench.py --shard views                          (ONE shape split by view over the N GPUs)
+  python bench.py --impl reference ...                   (the reference on the host cores, rank 0)
 
-A "step" is one pass of the whole path over one shape per rank (weak scaling): a synthetic
-30 000-point coloured cloud + ~10k-triangle mesh + 1024^2 atlas, 8 views, DDNM 100 steps at
-256^2 (BASELINE.json configs[1]); random-init weights of the reference architecture.
-Prints ONE JSON line (rank 0).
+Default (what the driver runs): BASELINE configs[1] — a "step" is one pass of the whole path over
+one shape per rank (weak scaling): a synthetic 30 000-point coloured cloud + ~10k-triangle mesh +
+1024^2 atlas, 8 views, DDNM 100 steps at 256^2, random-init weights of the reference architecture
+(the checkpoint is not downloadable here).  Prints ONE JSON line (rank 0).  Beside the contract keys
+the line carries `roofline`, `cpu_baseline`, `e2e`, `gpu_baseline` (the reference's own sampler +
+UNetModel, stock PyTorch fp16, on the same GPU), `texture_psnr_db` (8-bit atlas vs the atlas made
+from the reference sampler's views, utils/metric_utils/psnr_ssmi.py:23-42) and `other_configs`
+(short measured runs of configs[0], [2], [3], [4]).
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -19,20 +26,62 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-V, RES, CAM_RES, ATLAS_RES, N_POINTS, T_STEPS = 8, 256, 512, 1024, 30000, 100
-F_UNET = 2.2397e12  # FLOPs of one U-Net forward at 256^2, batch 1
-WORKLOAD = "30k-pt synthetic cloud, view_num=8, DDNM_inpaint 256^2 (T_sampling=100), atlas 1024^2"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+DEMO_CLOUDS = ["clock", "cup", "PaulFrankLunchBox", "rolling_lion", "2ce6_chair"]
+
+# BASELINE.json configs[i] -> workload parameters.  S = shapes per step per GPU.
+CONFIGS = {
+    0: dict(workload="dataset/demo_data/clock.ply (30k pts), view_num=2, texture_gen_method='nearest' "
+                     "(no diffusion), proxy voxel-shell mesh, atlas 1024^2",
+            V=2, res=256, cam_res=512, R=1024, S=1, method="nearest", scene="clock"),
+    1: dict(workload="30k-pt synthetic cloud, view_num=8, DDNM_inpaint 256^2 (T_sampling=100), atlas 1024^2",
+            V=8, res=256, cam_res=512, R=1024, S=1, method="DDNM_inpaint", scene="synthetic"),
+    2: dict(workload="configs/default.yaml (NBF [21], complete_unseen_by neighbor, optimize_from ours) on "
+                     "the reference's demo clouds, proxy voxel-shell meshes, DDNM_inpaint 256^2, atlas 1024^2",
+            V=8, res=256, cam_res=512, R=1024, S=1, method="DDNM_inpaint", scene="demo", flow="default"),
+    3: dict(workload="batch of synthetic 30k-pt clouds, 8 views each, DDNM_inpaint 256^2, 8 shapes per GPU "
+                     "in one U-Net batch (64 shapes on 8 GPUs)",
+            V=8, res=256, cam_res=512, R=1024, S=8, method="DDNM_inpaint", scene="synthetic"),
+    4: dict(workload="dense 100k-pt noisy synthetic cloud (sigma 0.005), view_num=16, DDNM_inpaint 512^2 "
+                     "(ADM 512 preset), cam_res 1024, atlas 2048^2, one shape per GPU",
+            V=16, res=512, cam_res=1024, R=2048, S=1, method="DDNM_inpaint", scene="synthetic",
+            n_points=100000, noise_std=0.005),
+}
+T_STEPS = 100
+F_UNET_256 = 2.2397e12  # FLOPs of one U-Net forward at 256^2, batch 1
 
 
-def path_config(flow="path"):
+def path_config(c, flow=None):
     from pointdreamer_b200 import demo
-    # "path": configs/default.yaml with the two post-path "next" rows disabled (SURVEY §8d config 3,
-    # the north-star metric); "default": configs/default.yaml as shipped (complete_unseen_by:
-    # neighbor + optimize_from: ours run after the path)
-    cfg = dict(demo.DEFAULT_CONFIG, view_num=V, res=RES, cam_res=CAM_RES, xatlas_texture_res=ATLAS_RES)
+    flow = flow or c.get("flow", "path")
+    # "path": the metric's project -> inpaint -> unproject (complete_unseen_by 'unproject', no
+    # optimize_color); "default": configs/default.yaml as shipped (+ neighbour completion +
+    # optimize_color after the path)
+    cfg = dict(demo.DEFAULT_CONFIG, view_num=c["V"], res=c["res"], cam_res=c["cam_res"],
+               xatlas_texture_res=c["R"], texture_gen_method=c["method"])
     if flow == "path":
         cfg.update(complete_unseen_by="unproject", optimize_from=None)
-    return cfg
+    return cfg, flow
+
+
+def make_scenes(c, rank, world):
+    """numpy scene dicts this rank processes per step."""
+    from pointdreamer_b200 import synthetic
+    if c["scene"] == "clock":
+        return [synthetic.proxy_scene_from_ply(os.path.join(GOLDEN, "clock.ply"), G=40, atlas_res=c["R"])]
+    if c["scene"] == "demo":
+        names = [n for n in DEMO_CLOUDS if os.path.exists(_cloud_path(n))]
+        name = names[rank % len(names)]
+        return [synthetic.proxy_scene_from_ply(_cloud_path(name), G=40, atlas_res=c["R"])]
+    S = c["S"]
+    return [synthetic.make_scene(c.get("n_points", 30000), seed=rank * S + i,
+                                 noise_std=c.get("noise_std", 0.0), atlas_res=c["R"])
+            for i in range(S)]
+
+
+def _cloud_path(name):
+    p = os.path.join(GOLDEN, "clouds", name + ".ply")
+    return p if os.path.exists(p) else os.path.join(GOLDEN, name + ".ply")
 
 
 class ClockSampler:
@@ -68,7 +117,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
+        sm, smax, power, reasons = [], None, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             parts = [p.strip() for p in r.split(",")]
@@ -77,6 +126,7 @@ class ClockSampler:
             try:
                 sm.append(float(parts[0]))
                 smax = float(parts[1])
+                power.append(float(parts[2]))
             except ValueError:
                 continue
             for n, v in zip(names, parts[3:7]):
@@ -84,6 +134,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -95,84 +146,445 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback"
 
 
-def cpu_unet_forward_seconds(n_forwards=2):
-    """Reference U-Net restatement (oracle, fp32) on the host cores, batch 1 at 256^2."""
+def hbm_algorithmic_bytes(c, n_points, n_verts, n_faces):
+    """SURVEY §8d algorithmic bytes of the HBM-bound stages for one shape."""
+    V, res, cam, R = c["V"], c["res"], c["cam_res"], c["R"]
+    project = n_points * 24 + V * n_points * 4 + 3 * V * 3 * res * res * 4
+    raster = (n_verts + n_faces) * 12 + V * cam * cam * 9
+    unproject = R * R * 17 + V * cam * cam * 4 + V * 3 * res * res * 4 + n_faces * 12 + R * R * 17
+    fill_views = V * res * res * 32 if c["method"] == "nearest" else 0
+    fill_atlas = 2 * R * R * 16
+    return dict(project_splat=project, raster=raster, unproject_nbf=unproject,
+                fill_views=fill_views, fill_atlas=fill_atlas,
+                total=project + raster + unproject + fill_views + fill_atlas)
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (the oracle / the reference on the host cores)
+# ------------------------------------------------------------------------------------------
+def host_threads():
+    """All host cores, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers."""
     import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return n
+
+
+def cpu_unet(model_cfg, res):
+    """The reference's own UNetModel (fp32) when baseline/_ref or /root/reference is present,
+    else the oracle restatement.  Returns (callable(x, t), kind)."""
+    import torch
+    from oracle import ref_loader
     from oracle import unet as ounet
     from pointdreamer_b200.unet import random_state_dict
-    sd = random_state_dict(ounet.DEFAULT_CONFIG, seed=1234, device="cpu")
-    o = ounet.UNetOracle(sd, ounet.DEFAULT_CONFIG, emulate_fp16=False)
-    x = torch.randn(1, 3, RES, RES)
-    t = torch.tensor([500.0])
-    times = []
-    for _ in range(n_forwards):
-        t0 = time.time()
-        o.forward(x, t)
-        times.append(time.time() - t0)
-    return min(times), times
+    sd = random_state_dict(model_cfg, seed=1234, device="cpu")
+    if ref_loader.available():
+        from oracle import reference_ddnm as rd
+        model = rd.build_model(model_cfg, sd, "cpu", fp16=False)
+
+        def fwd(x, t):
+            with torch.no_grad():
+                return model(x, t)
+        return fwd, "reference"
+    o = ounet.UNetOracle(sd, model_cfg, emulate_fp16=False)
+    return o.forward, "port"
 
 
-def cpu_geometry_seconds(scene, cfg):
+def cpu_geometry_seconds(scene, cfg, c):
     """Oracle project/splat/unproject for ONE view, scaled by V by the caller."""
-    import numpy as np
     from oracle import camera as ocam, project as oproj, unproject as ounproj
-    cams, base_dirs, _, _ = ocam.create_cameras(V, 1.6, CAM_RES)
-    params = [c.params for c in cams][:1]
+    cams, base_dirs, _, _ = ocam.create_cameras(c["V"], 1.6, c["cam_res"])
+    params = [cm.params for cm in cams][:1]
     t0 = time.time()
     pr = oproj.project_vertices_points(params, scene["vertices"], scene["xyz"], True, 0.05)
-    depth, fidx, mask = oproj.rasterize(pr["pos"], scene["faces"], CAM_RES)
-    hm = oproj.resize_mask_half_any(mask, RES)
-    vis, _ = oproj.point_validation_by_depth(CAM_RES, pr["point_uvs"], pr["point_depths"], depth, 1e-4)
-    pp = oproj.point_pixels(pr["point_uvs"], RES)
-    sparse, m0, m2, scales = oproj.get_sparse_images(pp, scene["rgb"], vis, hm, 1, RES, 1, 1, 0.82)
+    depth, fidx, mask = oproj.rasterize(pr["pos"], scene["faces"], c["cam_res"])
+    hm = oproj.resize_mask_half_any(mask, c["res"])
+    vis, _ = oproj.point_validation_by_depth(c["cam_res"], pr["point_uvs"], pr["point_depths"], depth, 1e-4)
+    pp = oproj.point_pixels(pr["point_uvs"], c["res"])
+    sparse, m0, m2, scales = oproj.get_sparse_images(pp, scene["rgb"], vis, hm, 1, c["res"], 1, 1, 0.82)
     xa = scene["xatlas_dict"]
-    ounproj.unproject(sparse, scene["f_normals"], RES, params, CAM_RES, base_dirs[:1], xa["gb_pos"],
-                      xa["mask"], xa["per_atlas_pixel_face_id"], pr["uv_centers"], pr["uv_scales"],
-                      0.05, scales, depth, cfg["edge_dilate_kernels"], True)
+    ounproj.unproject(sparse, scene["f_normals"], c["res"], params, c["cam_res"], base_dirs[:1],
+                      xa["gb_pos"], xa["mask"], xa["per_atlas_pixel_face_id"], pr["uv_centers"],
+                      pr["uv_scales"], 0.05, scales, depth, cfg["edge_dilate_kernels"], True)
     return time.time() - t0
 
 
+def cpu_nearest_path(scene, cfg, c):
+    """configs[0] end to end on the host (oracle/pipeline.py).  Returns (seconds, atlas)."""
+    from oracle import pipeline
+    ocfg = dict(view_num=c["V"], res=c["res"], cam_res=c["cam_res"], crop_padding=0.05, point_size=1,
+                edge_point_size=1, mask_ratio_thresh=0.82,
+                edge_dilate_kernels=cfg["edge_dilate_kernels"], complete_unseen_by_projection=True)
+    t0 = time.time()
+    out = pipeline.run_path(ocfg, scene)
+    return time.time() - t0, out["atlas_dilated"]
+
+
+def cpu_baseline_ddnm(c, cfg, scene, model_cfg, n_forwards, warm=0):
+    import torch
+    cores = host_threads()
+    fwd, kind = cpu_unet(model_cfg, c["res"])
+    x = torch.randn(1, 3, c["res"], c["res"])
+    t = torch.tensor([500.0])
+    for _ in range(warm):
+        fwd(x, t)
+    times = []
+    for _ in range(n_forwards):
+        t0 = time.time()
+        fwd(x, t)
+        times.append(time.time() - t0)
+    t_fwd = sum(times) / len(times)
+    t_geom = cpu_geometry_seconds(scene, cfg, c)
+    per_shape = c["V"] * T_STEPS * t_fwd + c["V"] * t_geom
+    what = "the reference's own UNetModel" if kind == "reference" else "oracle U-Net port"
+    sample = (f"{n_forwards} forwards of {what} (fp32, batch 1, {c['res']}^2: {t_fwd:.2f} s mean) of the "
+              f"{c['V'] * T_STEPS} per shape + oracle project/unproject of 1 of {c['V']} views "
+              f"({t_geom:.1f} s); shapes/s extrapolated = 1/({c['V'] * T_STEPS}*t_fwd + {c['V']}*t_geom)")
+    return dict(value=1.0 / per_shape, unit="shapes/s", cores=cores, kind=kind, sample=sample,
+                seconds_per_forward=t_fwd), t_fwd
+
+
 def run_reference(args):
-    """--impl reference: the reference algorithm (oracle restatement; the reference itself is
-    pure Python + third-party CUDA packages that are not installable here) on the host cores."""
+    """--impl reference: the reference's CPU execution of the path on ALL host cores (rank 0 only):
+    its own UNetModel through oracle/ref_loader.py when present (else the oracle port) for the DDNM
+    configs, the oracle pipeline end to end for configs[0]."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    from pointdreamer_b200 import synthetic
-    cores = torch.get_num_threads()
-    cfg = path_config()
-    scene = synthetic.make_scene(N_POINTS, seed=0, atlas_res=ATLAS_RES)
-    t_geom_view = cpu_geometry_seconds(scene, cfg)
-    from oracle import unet as ounet
-    from pointdreamer_b200.unet import random_state_dict
-    sd = random_state_dict(ounet.DEFAULT_CONFIG, seed=1234, device="cpu")
-    o = ounet.UNetOracle(sd, ounet.DEFAULT_CONFIG, emulate_fp16=False)
-    x = torch.randn(1, 3, RES, RES)
-    t = torch.tensor([500.0])
-    for _ in range(min(args.warmup, 1)):
-        o.forward(x, t)
-    times = []
-    for _ in range(args.steps):
-        t0 = time.time()
-        o.forward(x, t)
-        times.append(time.time() - t0)
-    t_fwd = sum(times) / len(times)
-    per_shape = V * T_STEPS * t_fwd + V * t_geom_view
-    value = 1.0 / per_shape
-    sample = (f"each step = 1 U-Net forward (batch 1, fp32, 256^2) of the {V * T_STEPS} per shape; "
-              f"+ oracle project/unproject of 1 of {V} views timed once ({t_geom_view:.1f} s); "
-              f"shapes/s extrapolated = 1/({V * T_STEPS}*t_fwd + {V}*t_geom_view)")
+    c = CONFIGS[args.config]
+    cfg, flow = path_config(c, args.flow)
+    scene = make_scenes(dict(c, S=1), 0, 1)[0]
+    if c["method"] == "nearest":
+        cores = host_threads()
+        times = []
+        for _ in range(max(1, min(args.steps, 3))):
+            s, _ = cpu_nearest_path(scene, cfg, c)
+            times.append(s)
+        per_shape = sum(times) / len(times)
+        cb = dict(value=1.0 / per_shape, unit="shapes/s", cores=cores, kind="port",
+                  sample=f"{len(times)} whole shapes through oracle/pipeline.py (numpy restatement of the "
+                         f"reference's nearest flow; its third-party CUDA/C++ dependencies are absent)")
+        ms = per_shape * 1e3
+    else:
+        from pointdreamer_b200.unet import DEFAULT_MODEL_CONFIG, channel_mult_for
+        model_cfg = dict(DEFAULT_MODEL_CONFIG, image_size=c["res"], channel_mult=channel_mult_for(c["res"]))
+        cb, t_fwd = cpu_baseline_ddnm(c, cfg, scene, model_cfg, max(1, args.steps), warm=min(args.warmup, 1))
+        ms = t_fwd * 1e3
     print(json.dumps({
-        "impl": "reference", "metric": "shapes/sec", "value": value, "unit": "shapes/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_fwd * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "weights": "random-init ADM 256x256 architecture"},
-        "cpu_baseline": {"value": value, "unit": "shapes/s", "cores": cores, "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": value, "unit": "shapes/s", "h2d_bytes_per_step": 0,
+        "impl": "reference", "metric": "shapes/sec", "value": cb["value"], "unit": "shapes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": c["workload"], "baseline_config": args.config,
+                   "weights": "random-init ADM architecture", "host_threads": cb["cores"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "shapes/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+class Bench:
+    def __init__(self, args, config_id, rank, local_rank, world, dev, shard="shapes", flow=None):
+        import numpy as np
+        import torch
+        from pointdreamer_b200 import demo
+        from pointdreamer_b200.ddnm_inpainting import Inpainter
+        from pointdreamer_b200.unet import DEFAULT_MODEL_CONFIG, channel_mult_for
+        self.torch, self.np, self.demo = torch, np, demo
+        self.c = c = CONFIGS[config_id]
+        self.config_id, self.rank, self.world, self.dev, self.shard = config_id, rank, world, dev, shard
+        self.cfg, self.flow = path_config(c, flow)
+        self.S = c["S"]
+        # --shard views: every rank holds the SAME shape (rank 0's) and runs V/world of its chains
+        self.scenes_np = make_scenes(c, 0 if shard == "views" else rank, world)
+
+        def pin(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+        self.scenes_host, self.scenes_dev = [], []
+        for sc in self.scenes_np:
+            h = {k: pin(v) for k, v in sc.items() if k != "xatlas_dict"}
+            h["xatlas_dict"] = {k: pin(v) for k, v in sc["xatlas_dict"].items()}
+            d = {k: v.to(dev) for k, v in h.items() if k != "xatlas_dict"}
+            d["xatlas_dict"] = {k: v.to(dev) for k, v in h["xatlas_dict"].items()}
+            self.scenes_host.append(h)
+            self.scenes_dev.append(d)
+        self.inpainter = None
+        self.model_cfg = None
+        if c["method"] == "DDNM_inpaint":
+            self.model_cfg = dict(DEFAULT_MODEL_CONFIG, image_size=c["res"],
+                                  channel_mult=channel_mult_for(c["res"]))
+            self.inpainter = Inpainter(dev, model_config=self.model_cfg, seed=42, offset=0,
+                                       allow_random_weights=True)
+        self.cam_info = demo.prepare_cameras(self.cfg, dev)
+        self.keys = {k: self.cfg[k] for k in demo.PATH_CONFIG_KEYS}
+
+    # ---- one pass of the path with inputs resident in HBM ----
+    def colorize(self, sc, stage_events=None, inpainter="default"):
+        inp = self.inpainter if inpainter == "default" else inpainter
+        return self.demo.colorize_one_mesh(
+            sc["xyz"], sc["rgb"], sc["vertices"], sc["faces"], sc["f_normals"], sc["xatlas_dict"],
+            self.cam_info, device=self.dev, save_img_path=None, inpainter=inp, glctx=None,
+            logger=None, stage_events=stage_events, **self.keys)[4]
+
+    def step_device(self):
+        from pointdreamer_b200 import dist as pdist
+        torch = self.torch
+        if self.inpainter is not None:
+            self.inpainter.chains_done = 0
+        if self.shard == "views":
+            return self.step_views_sharded()
+        if self.S > 1:
+            atlas = torch.stack(self.demo.colorize_batch(self.scenes_dev, self.cam_info, self.cfg,
+                                                         self.inpainter, self.dev))
+        else:
+            atlas = self.colorize(self.scenes_dev[0])[None]
+        if self.world > 1:  # the one collective of the path: assemble every rank's atlases
+            atlas = pdist.gather_blocks(atlas)
+        return atlas
+
+    def step_views_sharded(self):
+        """ONE shape, its V chains split over the ranks: PROJECT replicated (tiny), DDNM on the
+        local block of views, one all-gather of the views, UNPROJECT on every rank."""
+        from pointdreamer_b200 import dist as pdist
+
+        class Sharded:
+            def __init__(s, inp):
+                s.inp = inp
+
+            def inpaint_batch(s, sparse, masks, chain0=None):
+                return pdist.inpaint_views_sharded(s.inp, sparse, masks)
+
+        return self.colorize(self.scenes_dev[0], inpainter=Sharded(self.inpainter))[None]
+
+    # ---- the same through HOST buffers (pinned inputs in, atlas out) ----
+    def step_e2e(self):
+        torch, demo = self.torch, self.demo
+        if self.inpainter is not None:
+            self.inpainter.chains_done = 0
+        if self.S == 1 and self.shard == "shapes":
+            return demo.colorize_from_host(self.scenes_host[0], self.cam_info, self.cfg,
+                                           self.inpainter, self.dev)
+        h2d = 0
+        scenes = []
+        for h in (self.scenes_host if self.shard == "shapes" else self.scenes_host[:1]):
+            d = {k: v.to(self.dev, non_blocking=True) for k, v in h.items() if k != "xatlas_dict"}
+            d["xatlas_dict"] = {k: v.to(self.dev, non_blocking=True) for k, v in h["xatlas_dict"].items()}
+            d["xatlas_dict"]["_pdr_num_texels"] = int(h["xatlas_dict"]["mask"].sum())
+            h2d += sum(t.numel() * t.element_size() for t in h.values() if torch.is_tensor(t))
+            h2d += sum(t.numel() * t.element_size() for t in h["xatlas_dict"].values())
+            scenes.append(d)
+        if self.shard == "views":
+            saved, self.scenes_dev = self.scenes_dev, scenes
+            atlas = self.step_views_sharded()
+            self.scenes_dev = saved
+        else:
+            atlas = torch.stack(demo.colorize_batch(scenes, self.cam_info, self.cfg, self.inpainter,
+                                                    self.dev))
+        host = torch.empty(atlas.shape, dtype=atlas.dtype, pin_memory=True)
+        host.copy_(atlas, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host, h2d, atlas.numel() * atlas.element_size()
+
+    def stage_breakdown(self):
+        torch = self.torch
+        evs = []
+        if self.inpainter is not None:
+            self.inpainter.chains_done = 0
+        self.colorize(self.scenes_dev[0], stage_events=evs)
+        torch.cuda.synchronize()
+        return {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(evs[:-1], evs[1:])}
+
+    # ---- timed run ----
+    def run(self, steps, warmup, profile=True, e2e=True):
+        import torch.distributed as dist
+        from pointdreamer_b200 import _lib
+        from pointdreamer_b200.unet import profile_begin, profile_end
+        torch, dev, world = self.torch, self.dev, self.world
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def max_over_ranks(ms):
+            if world == 1:
+                return ms
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        for _ in range(warmup):
+            self.step_device()
+        barrier()
+        sampler = ClockSampler(dev.index or 0)
+        if self.rank == 0:
+            sampler.start()
+        prof_on = profile and self.inpainter is not None
+        if prof_on:
+            profile_begin(self.inpainter.model, every=25, max_forwards=4 * steps + 4)
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            atlas = self.step_device()
+        e1.record()
+        barrier()
+        ms_step = max_over_ranks(e0.elapsed_time(e1)) / steps
+        launches = _lib.launch_count() - l0
+        prof, n_fwd = profile_end(self.inpainter.model) if prof_on else (None, 0)
+        clocks = sampler.stop() if self.rank == 0 else None
+        shapes_per_step = (1 if self.shard == "views" else world * self.S)
+        out = dict(ms_per_step=ms_step, value=shapes_per_step * 1000.0 / ms_step, launches=launches,
+                   prof=prof, n_fwd=n_fwd, clocks=clocks, atlas=atlas,
+                   shapes_per_step=shapes_per_step)
+        if e2e:
+            self.step_e2e()
+            barrier()
+            t0 = time.time()
+            for _ in range(steps):
+                atlas_host, h2d, d2h = self.step_e2e()
+            barrier()
+            e2e_ms = max_over_ranks((time.time() - t0) * 1e3) / steps
+            out["e2e"] = {"value": shapes_per_step * 1000.0 / e2e_ms, "unit": "shapes/s",
+                          "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        return out
+
+    def roofline(self, r):
+        peak_tf, peak_hbm, peak_src = measured_peaks()
+        c = self.c
+        if self.inpainter is None:
+            sc = self.scenes_np[0]
+            b = hbm_algorithmic_bytes(c, len(sc["xyz"]), len(sc["vertices"]), len(sc["faces"]))
+            gbs = b["total"] / (r["ms_per_step"] * 1e-3) / 1e9
+            return {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s",
+                    "frac": gbs / peak_hbm, "traffic": None,
+                    "kernel": "whole step (about 40 small launches; no single dominant kernel: "
+                              "per-kernel GB/s in profiles/r02_geometry_kernels.md)",
+                    "algorithmic_bytes_per_shape": b, "peak_source": f"{peak_src} hbm_gbs"}
+        prof = r["prof"]
+        conv = prof["conv_tc"]
+        conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+        total_prof_ms = sum(v["ms"] for v in prof.values())
+        traffic, traffic_src = None, None
+        cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_traffic.json")))
+        if cands and self.config_id in (1, 2, 3):  # DRAM bytes per conv launch, newest ncu capture
+            tj = json.load(open(cands[-1]))
+            traffic, traffic_src = tj["avg_traffic_bytes_per_launch"], tj["source"]
+        n_fwd = max(r["n_fwd"], 1)
+        flops_fwd = sum(v["flops"] for v in prof.values()) / n_fwd  # per batched forward
+        forwards_per_step = T_STEPS
+        return {
+            "bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": conv_tflops / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
+            "kernel": "conv_halo_kernel / conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv: "
+                      "halo-tile 3x3, 2-CTA and 1-CTA)",
+            "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
+            "launch_avg_ms": conv["ms"] / max(conv["launches"], 1),
+            "flops_per_launch_avg": conv["flops"] / max(conv["launches"], 1),
+            "share_of_unet_time": conv["ms"] / total_prof_ms if total_prof_ms else None,
+            "sampled_forwards": r["n_fwd"],
+            "per_class_ms_per_forward": {k: v["ms"] / n_fwd for k, v in prof.items()},
+            "whole_path_frac_of_tensor_roofline":
+                (forwards_per_step * flops_fwd / (r["ms_per_step"] * 1e-3) / 1e12) / peak_tf,
+        }
+
+
+def gpu_reference_leg(b, ours_atlas):
+    """The reference's own execution style on the SAME GPU: its unmodified
+    Inpainter.inpaint loop - serial views, batch 1, stock PyTorch fp16 + cuDNN, host round trip
+    per step (ours_utils.py:914-929, diffusion.py:459-570) - on the same sparse images, weights and
+    noise seed; its views then go through the same UNPROJECT, which gives the texture PSNR of our
+    atlas against the reference sampler's atlas (8-bit, psnr_ssmi.py:23-42)."""
+    import torch
+    from oracle import ref_loader
+    if not ref_loader.available():
+        return None, None
+    from oracle import reference_ddnm as rd
+    from pointdreamer_b200 import metrics
+    from pointdreamer_b200.unet import random_state_dict
+    c, dev = b.c, b.dev
+    sd = random_state_dict(b.model_cfg, seed=1234, device=dev)
+    model = rd.build_model(b.model_cfg, sd, dev, fp16=True)
+    del sd
+    runner = rd.build_runner(dev, image_size=c["res"], T_sampling=T_STEPS)
+    ref_inp = rd.reference_inpainter(runner, model)
+    torch.backends.cudnn.benchmark = False
+    times = {}
+
+    class RefAdapter:  # Inpainter-shaped: colorize_one_mesh calls inpaint_batch(sparse, mask)
+        def inpaint_batch(self, sparse, masks, chain0=None):
+            m3 = masks[:, None].repeat(1, 3, 1, 1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            e0.record()
+            out = rd.run_views(ref_inp, sparse, m3, seed=42)
+            e1.record()
+            torch.cuda.synchronize()
+            times["wall_s"] = time.time() - t0
+            times["device_s"] = e0.elapsed_time(e1) / 1e3
+            return out
+
+    with torch.no_grad():
+        ref_atlas = b.colorize(b.scenes_dev[0], inpainter=RefAdapter())
+    torch.cuda.synchronize()
+    a8 = metrics.atlas_to_uint8(ours_atlas.cpu().numpy())
+    r8 = metrics.atlas_to_uint8(ref_atlas.cpu().numpy())
+    psnr = metrics.calculate_psnr(a8, r8)
+    err = (ours_atlas - ref_atlas).abs()
+    gb = {"value": 1.0 / times["wall_s"], "unit": "shapes/s", "kind": "reference",
+          "seconds_per_shape": times["wall_s"],
+          "what": f"the reference's own Inpainter.inpaint loop ({c['V']} serial views x {T_STEPS} steps, "
+                  "batch 1, stock PyTorch fp16/cuDNN, host round trip per step) on the same B200, same "
+                  "weights / sparse images / noise seed; geometry stages are ours (< 2 % of its time)"}
+    tex = {"texture_psnr_db": psnr, "atlas_max_abs_err": float(err.max()),
+           "atlas_mean_abs_err": float(err.mean()),
+           "atlas_8bit_levels_differing_frac": float((a8 != r8).mean()),
+           "vs": "atlas unprojected from the views of the reference's own sampler + UNetModel on this GPU"}
+    del model
+    torch.cuda.empty_cache()
+    return gb, tex
+
+
+def short_run(args, config_id, rank, local_rank, world, dev):
+    """`other_configs` entry: 1 warm-up + 1 timed step of another BASELINE config."""
+    import torch
+    try:
+        b = Bench(args, config_id, rank, local_rank, world, dev)
+        r = b.run(steps=1, warmup=1, profile=b.inpainter is not None, e2e=False)
+        rf = b.roofline(r) if rank == 0 else None
+        entry = None
+        if rank == 0:
+            entry = {"workload": b.c["workload"], "flow": b.flow, "value": r["value"], "unit": "shapes/s",
+                     "ms_per_step": r["ms_per_step"], "steps": 1, "warmup": 1, "n_gpus": world,
+                     "shapes_per_step": r["shapes_per_step"], "gpu_launches": r["launches"],
+                     "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "unit", "frac")
+                                  if k in rf}}
+            if "whole_path_frac_of_tensor_roofline" in rf:
+                entry["roofline"]["whole_path_frac"] = rf["whole_path_frac_of_tensor_roofline"]
+            if b.inpainter is None and world == 1:
+                entry["stage_ms"] = b.stage_breakdown()
+                secs, ref_atlas = cpu_nearest_path(b.scenes_np[0], b.cfg, b.c)
+                from pointdreamer_b200 import metrics
+                a8 = metrics.atlas_to_uint8(r["atlas"][0].cpu().numpy())
+                r8 = metrics.atlas_to_uint8(ref_atlas)
+                entry["texture_psnr_db"] = metrics.calculate_psnr(a8, r8)
+                entry["atlas_equal_to_oracle"] = bool((r["atlas"][0].cpu().numpy() == ref_atlas).all())
+                entry["cpu_baseline"] = {"value": 1.0 / secs, "unit": "shapes/s", "cores": host_threads(),
+                                         "kind": "port", "sample": "1 whole shape through oracle/pipeline.py"}
+        del b
+        torch.cuda.empty_cache()
+        return entry
+    except Exception as e:  # an extra must never take the headline line down
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
 def main():
@@ -181,25 +593,26 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS),
+                    help="index into BASELINE.json configs (default 1, the config the metric is quoted on)")
+    ap.add_argument("--shard", default="shapes", choices=["shapes", "views"],
+                    help="shapes: every rank its own shape(s) (weak scaling); views: ONE shape, its "
+                         "diffusion chains split by view over the ranks (latency per shape, strong scaling)")
+    ap.add_argument("--flow", default=None, choices=["path", "default"],
+                    help="path = project->inpaint->unproject (the metric); default = configs/default.yaml "
+                         "as shipped, i.e. + neighbour completion + optimize_color")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shapes-per-gpu", type=int, default=1,
-                    help="shapes per step per GPU (default 1 = BASELINE configs[1]; 8 with --gpus 8 "
-                         "= configs[3], all chains of a GPU in one U-Net batch)")
-    ap.add_argument("--flow", default="path", choices=["path", "default"],
-                    help="path = project->inpaint->unproject (the metric); default = configs/"
-                         "default.yaml as shipped, i.e. + neighbour completion + optimize_color")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other_configs short runs")
+    ap.add_argument("--shapes-per-gpu", type=int, default=None, help="override S of the config")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
-    from pointdreamer_b200 import _lib, demo, synthetic
-    from pointdreamer_b200 import dist as pdist
-    from pointdreamer_b200.ddnm_inpainting import Inpainter
-    from pointdreamer_b200.unet import profile_begin, profile_end
+    from pointdreamer_b200 import _lib
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -211,168 +624,70 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    if args.shapes_per_gpu:
+        CONFIGS[args.config] = dict(CONFIGS[args.config], S=args.shapes_per_gpu)
 
-    cfg = path_config(args.flow)
-    # ---- setup (untimed): inputs in pinned host memory, weights, cameras ----
-    S = args.shapes_per_gpu
-    scene_np = synthetic.make_scene(N_POINTS, seed=rank * S, atlas_res=ATLAS_RES)
-    extra_dev = []
-    for i in range(1, S):
-        e = synthetic.make_scene(N_POINTS, seed=rank * S + i, atlas_res=ATLAS_RES)
-        d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in e.items() if k != "xatlas_dict"}
-        d["xatlas_dict"] = {k: torch.from_numpy(v).to(dev) for k, v in e["xatlas_dict"].items()}
-        extra_dev.append(d)
+    b = Bench(args, args.config, rank, local_rank, world, dev, shard=args.shard, flow=args.flow)
+    r = b.run(args.steps, args.warmup)
+    stage_ms = b.stage_breakdown() if (b.S == 1 and args.shard == "shapes") else None
+    c = b.c
 
-    def pin(a):
-        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-
-    scene_host = {k: pin(v) for k, v in scene_np.items() if k != "xatlas_dict"}
-    scene_host["xatlas_dict"] = {k: pin(v) for k, v in scene_np["xatlas_dict"].items()}
-    scene_dev = {k: v.to(dev) for k, v in scene_host.items() if k != "xatlas_dict"}
-    xa_dev = {k: v.to(dev) for k, v in scene_host["xatlas_dict"].items()}
-    inpainter = Inpainter(dev, seed=42, offset=0, allow_random_weights=True)
-    cam_info = demo.prepare_cameras(cfg, dev)
-    keys = {k: cfg[k] for k in demo.PATH_CONFIG_KEYS}
-
-    def step_device():
-        inpainter.chains_done = 0
-        if S > 1:
-            first = dict(scene_dev, xatlas_dict=xa_dev)
-            atlas = torch.stack(demo.colorize_batch([first] + extra_dev, cam_info, cfg, inpainter, dev))
-            if world > 1:
-                atlas = pdist.gather_stacked(atlas, world * S)
-            return atlas
-        out = demo.colorize_one_mesh(scene_dev["xyz"], scene_dev["rgb"], scene_dev["vertices"],
-                                     scene_dev["faces"], scene_dev["f_normals"], xa_dev, cam_info,
-                                     device=dev, save_img_path=None, inpainter=inpainter,
-                                     glctx=None, logger=None, **keys)
-        atlas = out[4]
-        if world > 1:  # the one collective of the path: assemble every rank's atlas
-            atlas = pdist.gather_stacked(atlas[None], world)
-        return atlas
-
-    def step_e2e():
-        inpainter.chains_done = 0
-        atlas_host, h2d, d2h = demo.colorize_from_host(scene_host, cam_info, cfg, inpainter, dev)
-        return atlas_host, h2d, d2h
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- leg 1: inputs resident in HBM ----
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local_rank)
+    line = None
     if rank == 0:
-        sampler.start()
-    profile_begin(inpainter.model, every=25, max_forwards=4 * args.steps + 4)
-    l0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        atlas = step_device()
-    e1.record()
-    barrier()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = _lib.launch_count() - l0
-    prof, n_fwd = profile_end(inpainter.model)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = ms_total / args.steps
-    value = world * S * 1000.0 / ms_per_step
-
-    # ---- leg 2: end to end through the public API with HOST buffers ----
-    step_e2e()
-    barrier()
-    t0 = time.time()
-    for _ in range(args.steps):
-        atlas_host, h2d, d2h = step_e2e()
-    barrier()
-    e2e_ms = max_over_ranks((time.time() - t0) * 1e3) / args.steps
-    e2e_value = world * 1000.0 / e2e_ms if S == 1 else None  # the host-buffer leg runs one shape
-
-    # ---- per-stage breakdown of one more (untimed) step: CUDA events at the stage boundaries ----
-    stage_ms = None
-    if S == 1:
-        evs = []
-        inpainter.chains_done = 0
-        demo.colorize_one_mesh(scene_dev["xyz"], scene_dev["rgb"], scene_dev["vertices"],
-                               scene_dev["faces"], scene_dev["f_normals"], xa_dev, cam_info,
-                               device=dev, save_img_path=None, inpainter=inpainter, glctx=None,
-                               logger=None, stage_events=evs, **keys)
-        torch.cuda.synchronize()
-        stage_ms = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(evs[:-1], evs[1:])}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peak_tf, peak_hbm, peak_src = measured_peaks()
-    conv = prof["conv_tc"]
-    conv_tflops = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
-    total_prof_ms = sum(v["ms"] for v in prof.values())
-    traffic, traffic_src = None, None
-    import glob
-    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_traffic.json")))
-    tp = cands[-1] if cands else ""
-    if tp:  # DRAM bytes per conv launch from the newest committed ncu capture
-        tj = json.load(open(tp))
-        traffic, traffic_src = tj["avg_traffic_bytes_per_launch"], tj["source"]
-    roofline = {
-        "bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-        "frac": conv_tflops / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
-        "kernel": "conv_halo_kernel / conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv: halo-tile 3x3, 2-CTA and 1-CTA)",
-        "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
-        "launch_avg_ms": conv["ms"] / max(conv["launches"], 1),
-        "flops_per_launch_avg": conv["flops"] / max(conv["launches"], 1),
-        "share_of_unet_time": conv["ms"] / total_prof_ms if total_prof_ms else None,
-        "sampled_forwards": n_fwd,
-        "per_class_ms_per_forward": {k: v["ms"] / max(n_fwd, 1) for k, v in prof.items()},
-        "whole_path_frac_of_tensor_roofline":
-            (S * V * T_STEPS * F_UNET / (ms_per_step * 1e-3) / 1e12) / peak_tf,
-    }
-    cpu_baseline = None
-    if world == 1 and not args.no_cpu_baseline:
-        t_fwd, all_t = cpu_unet_forward_seconds(2)
-        t_geom = cpu_geometry_seconds(scene_np, cfg)
-        per_shape = V * T_STEPS * t_fwd + V * t_geom
-        cpu_baseline = {
-            "value": 1.0 / per_shape, "unit": "shapes/s", "cores": torch.get_num_threads(),
-            "kind": "port",
-            "sample": (f"2 oracle U-Net forwards (fp32, batch 1, 256^2: {t_fwd:.2f} s best) of the "
-                       f"{V * T_STEPS} per shape + oracle project/unproject of 1 of {V} views "
-                       f"({t_geom:.1f} s); extrapolated to a whole shape")}
-    line = {
-        "metric": "shapes/sec", "value": value, "unit": "shapes/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "shapes_per_step_per_gpu": S, "flow": args.flow,
-                   "weights": "random-init ADM 256x256 architecture (552.8M params)",
-                   "point_validation_by_o3d": cfg["point_validation_by_o3d"],
-                   "complete_unseen_by": cfg["complete_unseen_by"],
-                   "optimize_from": cfg["optimize_from"], "edge_dilate_kernels": cfg["edge_dilate_kernels"],
-                   "l2": "working set (1.9 GB U-Net arena per step) is far larger than the 126 MB L2"},
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "shapes/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches,
-        "stage_ms": stage_ms,
-        "roofline": roofline,
-        "cpu_baseline": cpu_baseline,
-    }
-    print(json.dumps(line))
+        line = {
+            "metric": "shapes/sec", "value": r["value"], "unit": "shapes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong" if args.shard == "views" else "weak",
+            "vs_baseline": None, "dtype": "fp16" if b.inpainter is not None else "f32",
+            "data": "synthetic" if c["scene"] == "synthetic" else
+                    "reference demo clouds (tests/golden) + synthetic proxy meshes / random-init weights",
+            "config": {"workload": c["workload"], "baseline_config": args.config,
+                       "shapes_per_step_per_gpu": b.S, "shard": args.shard, "flow": b.flow,
+                       "weights": "random-init ADM architecture (552.8M params at 256^2)"
+                                  if b.inpainter is not None else None,
+                       "synthetic_weights": bool(b.inpainter.synthetic_weights) if b.inpainter else None,
+                       "point_validation_by_o3d": b.cfg["point_validation_by_o3d"],
+                       "complete_unseen_by": b.cfg["complete_unseen_by"],
+                       "optimize_from": b.cfg["optimize_from"],
+                       "edge_dilate_kernels": b.cfg["edge_dilate_kernels"],
+                       "l2": "working set (1.9 GB U-Net arena per step) is far larger than the 126 MB L2"
+                             if b.inpainter is not None else
+                             "inputs + outputs of a step (about 150 MB) exceed the 126 MB L2"},
+            "clocks": r["clocks"], "e2e": r["e2e"], "gpu_launches": r["launches"],
+            "stage_ms": stage_ms, "roofline": b.roofline(r),
+        }
+    # ---- baselines beside the number (N = 1 only) ----
+    if world == 1 and args.shard == "shapes":
+        if b.inpainter is not None and not args.no_gpu_baseline and b.S == 1:
+            gb, tex = gpu_reference_leg(b, r["atlas"][0])
+            line["gpu_baseline"] = gb
+            if tex:
+                line["texture_psnr_db"] = tex.pop("texture_psnr_db")
+                line["texture_parity"] = tex
+        if not args.no_cpu_baseline:
+            if b.inpainter is not None:
+                line["cpu_baseline"], _ = cpu_baseline_ddnm(c, b.cfg, b.scenes_np[0], b.model_cfg, 2)
+            else:
+                secs, ref_atlas = cpu_nearest_path(b.scenes_np[0], b.cfg, c)
+                from pointdreamer_b200 import metrics
+                line["cpu_baseline"] = {"value": 1.0 / secs, "unit": "shapes/s", "cores": host_threads(),
+                                        "kind": "port",
+                                        "sample": "1 whole shape through oracle/pipeline.py"}
+                line["texture_psnr_db"] = metrics.calculate_psnr(
+                    metrics.atlas_to_uint8(r["atlas"][0].cpu().numpy()), metrics.atlas_to_uint8(ref_atlas))
+    # ---- the other BASELINE configs, short runs (configs[0] / [2] need one GPU only) ----
+    if not args.no_extras and args.config == 1 and args.shard == "shapes":
+        del b
+        torch.cuda.empty_cache()
+        extras = {}
+        for cid in ([0, 2, 3, 4] if world == 1 else [3, 4]):
+            e = short_run(args, cid, rank, local_rank, world, dev)
+            if rank == 0:
+                extras[f"configs[{cid}]"] = e
+        if rank == 0:
+            line["other_configs"] = extras
+    if rank == 0:
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,10 +1,11 @@
 """Oracle (TEST INFRASTRUCTURE): import the reference's OWN source under a stub loader.
 
-Only usable where /root/reference exists (the build container).  It is how the numpy
-restatement in this package is pinned: `tests/golden/make_golden.py` runs the reference
-functions through this loader and commits their outputs as fixtures, and
-`tests/test_oracle_vs_reference.py` re-checks the restatement against the live reference when
-it is present.  Nothing here runs on the GPU box.
+Usable where /root/reference exists (the build container) or where oracle/make_ref.py has put
+its verbatim copy of the hot path's files under baseline/_ref/ (the GPU box).  It is how the
+numpy restatement in this package is pinned: `tests/golden/make_golden*.py` run the reference
+functions through this loader and commit their outputs as fixtures; on the GPU box
+`tests/test_ddnm_reference_chain_gpu.py` and bench.py's `gpu_baseline` leg run the reference's
+own sampler + UNetModel through it next to the CUDA path.
 
 The reference imports kaolin, nvdiffrast, open3d, trimesh, munch, kiui, matplotlib, ... which
 are not installed.  They are replaced by empty stub modules, and the FOUR third-party
@@ -28,7 +29,12 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PDR_REFERENCE_ROOT", "/root/reference")
+_REPO_REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                         "baseline", "_ref")
+# /root/reference in the build container; on the GPU box the verbatim copy of the hot path's
+# files that oracle/make_ref.py placed under baseline/_ref/ (git-ignored, shipped by gpurun)
+REFERENCE_ROOT = os.environ.get("PDR_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/pointdreamer") else _REPO_REF)
 
 _STUBS = [
     "kaolin", "kaolin.render", "kaolin.render.camera", "kaolin.metrics",

@@ -2,8 +2,9 @@
 all-gather at the end.
 
   * batch of shapes: shape i runs on rank i % world; finished atlases are all-gathered;
-  * one shape, G GPUs: view v's diffusion chain runs on rank v % G with the noise-stream slot of
-    chain v (chain0 = v), so the gathered views are bit-identical to a single-GPU run.
+  * one shape, G GPUs: rank r runs views r*V/G .. (r+1)*V/G-1 as one U-Net batch, each chain on
+    the noise-stream slot of its view (chain0 = first view), so the gathered views are
+    bit-identical to a single-GPU run.
 There is no per-step traffic; NCCL over NVLink on GPUs, gloo in the CPU tests.
 """
 import torch
@@ -39,14 +40,40 @@ def gather_stacked(local, n_items):
     return out.transpose(0, 1).reshape((n_items,) + tuple(local.shape[1:])).contiguous()
 
 
+def gather_blocks(local):
+    """All-gather per-rank stacks [n_local, ...] of BLOCK-sharded items (rank r owns items
+    r*n_local .. (r+1)*n_local-1) into item order on every rank."""
+    r, w = world()
+    if w == 1:
+        return local
+    local = local.contiguous()
+    out = torch.empty((w * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                      device=local.device)
+    dist.all_gather_into_tensor(out, local)
+    return out
+
+
+def view_block(n_views, rank=None, world_size=None):
+    """(first view, count) of the contiguous block of views this rank owns."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    if n_views % world_size != 0:
+        raise ValueError(f"{n_views} views do not shard evenly over {world_size} ranks")
+    n = n_views // world_size
+    return rank * n, n
+
+
 def inpaint_views_sharded(inpainter, sparse_imgs, masks):
-    """DDNM for one shape split by view across the ranks, then one all-gather of the views."""
+    """DDNM for ONE shape split by view across the ranks: rank r runs the contiguous
+    block of V/G chains it owns as ONE U-Net batch, with chain0 = its first view so every chain
+    keeps the slot of the reference's noise stream (diffusion.py:493-499, 552); then one
+    all-gather of the views.  The result equals the single-GPU run bit for bit."""
     r, w = world()
     V = sparse_imgs.shape[0]
     if w == 1:
         return inpainter.inpaint_batch(sparse_imgs, masks, chain0=0)
-    idx = shard_indices(V)
-    outs = []
-    for v in idx:  # chain0 = v keeps every chain on the noise slot the serial reference uses
-        outs.append(inpainter.inpaint_batch(sparse_imgs[v:v + 1], masks[v:v + 1], chain0=v))
-    return gather_stacked(torch.cat(outs, 0), V)
+    v0, n = view_block(V)
+    local = inpainter.inpaint_batch(sparse_imgs[v0:v0 + n].contiguous(),
+                                    masks[v0:v0 + n].contiguous(), chain0=v0)
+    return gather_blocks(local)

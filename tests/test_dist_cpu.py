@@ -26,14 +26,21 @@ def _worker(rank, world, port, q):
     full = pdist.gather_stacked(local, n)
     ok = all(bool((full[i] == i).all()) for i in range(n)) and full.shape == (n, 2, 3)
 
+    calls = []
+
     class FakeInpainter:
         def inpaint_batch(self, imgs, masks, chain0=None):
-            return imgs * 2 + chain0
+            calls.append((imgs.shape[0], chain0))
+            off = torch.arange(imgs.shape[0], dtype=torch.float32).reshape(-1, 1, 1, 1) + chain0
+            return imgs * 2 + off
 
     imgs = torch.arange(4 * 3 * 2 * 2, dtype=torch.float32).reshape(4, 3, 2, 2)
     out = pdist.inpaint_views_sharded(FakeInpainter(), imgs, torch.ones(4, 2, 2))
     expect = torch.stack([imgs[v] * 2 + v for v in range(4)])
     ok = ok and torch.equal(out, expect)
+    ok = ok and calls == [(2, 2 * rank)]  # the local views run as ONE batch on their noise slots
+    blocks = pdist.gather_blocks(torch.full((3, 2), float(rank)))
+    ok = ok and torch.equal(blocks, torch.tensor([0., 0, 0, 1, 1, 1])[:, None].repeat(1, 2))
     q.put((rank, ok, idx))
     dist.destroy_process_group()
 

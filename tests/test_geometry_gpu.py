@@ -141,3 +141,29 @@ def test_geometry_vs_oracle(cuda, seed, n_points, V, res, cam_res, R):
     assert int(mism.sum()) == 0, f"{int(mism.sum())} view-id mismatches of {mism.size}"
     assert np.array_equal(got["atlas_painted_mask"], painted)
     assert np.array_equal(got["atlas_img"], atlas)
+
+
+def test_unproject_without_crop_parameters(cuda):
+    """unproject.py:262-264: with uv_centers / uv_scales / inpaint_scale_factors / padding = None the
+    texel uv is plain ndc*0.5+0.5 and the crop arrays are never touched (NULL pointers in the ABI)."""
+    from oracle import camera as ocam, unproject as ounproj
+    from pointdreamer_b200 import camera, unproject as unproj
+    cfg, sc, g = load_geom_case("c")
+    V, res, cam_res = cfg["view_num"], cfg["res"], cfg["cam_res"]
+    cams, base_dirs, _, _ = camera.create_cameras(V, 1.6, cam_res, device=cuda)
+    xa = {k: _t(v, cuda) for k, v in sc["xatlas_dict"].items()}
+    views = _t(g["inpainted_nearest"], cuda)
+    depths = _t(g["mesh_depths"], cuda)
+    got = unproj.unproject(views, _t(sc["vertices"], cuda), _t(sc["f_normals"], cuda), res, cams,
+                           cam_res, base_dirs, xa["gb_pos"], xa["mask"],
+                           xa["per_atlas_pixel_face_id"], None, None, None, None, depths,
+                           cfg["edge_dilate_kernels"], None, False)
+    torch.cuda.synchronize()
+    ocams, obase, _, _ = ocam.create_cameras(V, 1.6, cam_res)
+    xan = sc["xatlas_dict"]
+    want = ounproj.unproject(g["inpainted_nearest"], sc["f_normals"], res, [c.params for c in ocams],
+                             cam_res, obase, xan["gb_pos"], xan["mask"],
+                             xan["per_atlas_pixel_face_id"], None, None, None, None,
+                             g["mesh_depths"], cfg["edge_dilate_kernels"], False)
+    for a, b, name in zip(got, want, ["atlas", "shrinked_vis", "view_ids", "coords", "points", "painted"]):
+        assert np.array_equal(a.cpu().numpy(), b), name
