@@ -169,12 +169,16 @@ int pdr_project(const float* cam_params, const float* vertices, int Vm, const fl
 
 /* Z-buffer rasteriser of the mesh for all views.  Replaces nvdiffrast.torch.rasterize as
  * used at ours_utils.py:142-147 plus the 512->256 mask resize of demo.py:103-104.
- *   pos [V,Vm,4] fp32 ; faces [F,3] int32 ; ws_keys: uint64[V*res*res] scratch
+ * Tile-binned: triangles are binned into 32 x 8 pixel tiles, one CTA per tile walks its bin from
+ * shared memory with one thread per pixel (no atomics on the z-buffer).
+ *   pos [V,Vm,4] fp32 ; faces [F,3] int32 ;
+ *   workspace: pdr_rasterize_workspace_bytes(V, F, res) bytes, 16-byte aligned
  *   depth [V,res,res] fp32 (0 empty) ; face_idx [V,res,res] int64 (-1 empty) ;
  *   mask_cam [V,res,res] u8 ; mask_out [V,out_res,out_res] u8 (out_res == res or res/2) */
+size_t pdr_rasterize_workspace_bytes(int V, int F, int res);
 int pdr_rasterize(const float* pos, const int* faces, int V, int Vm, int F, int res, int out_res,
-                  unsigned long long* ws_keys, float* depth, long long* face_idx,
-                  uint8_t* mask_cam, uint8_t* mask_out, void* stream);
+                  void* workspace, float* depth, long long* face_idx, uint8_t* mask_cam,
+                  uint8_t* mask_out, void* stream);
 
 /* 2x mask reduction.  Replaces demo.py:103-104 (torchvision Resize, bilinear without antialias,
  * then .bool()  ==  OR of each 2x2 block).  mask_in [V,res_in,res_in] u8 -> [V,res_in/2,res_in/2] */

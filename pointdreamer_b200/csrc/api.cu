@@ -174,13 +174,16 @@ int pdr_project(const float* cam_params, const float* vertices, int Vm, const fl
                         (cudaStream_t)stream);
 }
 
+size_t pdr_rasterize_workspace_bytes(int V, int F, int res) {
+  return rasterize_workspace_bytes(V, F, res);
+}
 int pdr_rasterize(const float* pos, const int* faces, int V, int Vm, int F, int res, int out_res,
-                  unsigned long long* ws_keys, float* depth, long long* face_idx,
-                  uint8_t* mask_cam, uint8_t* mask_out, void* stream) {
-  PDR_CHECK_ARG(pos && faces && ws_keys && depth && face_idx && mask_cam && mask_out,
+                  void* workspace, float* depth, long long* face_idx, uint8_t* mask_cam,
+                  uint8_t* mask_out, void* stream) {
+  PDR_CHECK_ARG(pos && faces && workspace && depth && face_idx && mask_cam && mask_out,
                 "pdr_rasterize: null pointer");
-  return rasterize_launch(pos, faces, V, Vm, F, res, out_res, ws_keys, depth, face_idx, mask_cam,
-                          mask_out, (cudaStream_t)stream);
+  return rasterize_launch(pos, faces, V, Vm, F, res, out_res, workspace, depth, face_idx,
+                          mask_cam, mask_out, (cudaStream_t)stream);
 }
 
 int pdr_mask_half_any(const uint8_t* mask_in, int V, int res_in, uint8_t* mask_out, void* stream) {

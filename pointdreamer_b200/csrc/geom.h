@@ -12,8 +12,9 @@ int project_launch(const float* cams, const float* vertices, int Vm, const float
                    float* vertice_uvs, float* uv_centers, float* uv_scales, float* point_uvs,
                    float* point_depths, cudaStream_t stream);
 
+size_t rasterize_workspace_bytes(int V, int F, int res);
 int rasterize_launch(const float* pos, const int* faces, int V, int Vm, int F, int res,
-                     int out_res, unsigned long long* ws_keys, float* depth, long long* face_idx,
+                     int out_res, void* workspace, float* depth, long long* face_idx,
                      uint8_t* mask_cam, uint8_t* mask_out, cudaStream_t stream);
 
 int mask_half_any_launch(const uint8_t* in, int V, int res_in, uint8_t* out, cudaStream_t stream);

@@ -6,47 +6,107 @@
 // Canonical tie rule (oracle/fill.py): minimum squared distance, then lowest linear index of
 // the source pixel.
 //
-// Two passes: (1) per column, distance to the nearest valid pixel above/below (sequential scan
-// down a column, coalesced across columns); (2) per pixel, walk columns outward (dx = 0, -1, +1,
-// ...) combining dx^2 with the column distances, stopping once dx^2 exceeds the best distance —
-// O(distance) probes per pixel instead of a kd-tree.
+// Two passes (an exact Euclidean distance transform with source tracking):
+//  (1) fill_column_kernel: per column, the SIGNED offset to the nearest valid pixel of that column
+//      (negative = above; on a tie the pixel above wins because it has the lower linear index), as
+//      one int16 per pixel.  A thread owns 32 consecutive rows of one column as a 32-bit mask and
+//      the per-column carries of the other segments go through shared memory, so the pass is fully
+//      parallel (no serial walk down the column) and its loads/stores are coalesced across columns.
+//  (2) fill_row_kernel: per pixel, min over columns c of (x-c)^2 + off(c)^2.  The row of offsets is
+//      staged in SHARED memory once per CTA; each thread walks outwards (dx = 0, -1, +1, ...) and
+//      stops once dx^2 exceeds the best distance - O(distance) shared-memory probes per pixel.
+// One candidate per column is enough: if the nearest pixels above and below are equally far the
+// upper one wins every tie-break, otherwise the nearer one strictly beats the other.
 #include "geom_common.cuh"
 #include <limits.h>
 #include "geom.h"
 
 namespace pdr {
 
-static constexpr int FILL_BIG = 1 << 20;
+static constexpr int FILL_NONE = 0x7FFF;   // int16 offset sentinel: the column has no valid pixel
+static constexpr int FILL_COLS = 32;       // columns per CTA in pass 1
+static constexpr int FILL_MAX_H = 8192;    // offsets must fit int16
 
-__global__ void fill_column_scan_kernel(const uint8_t* __restrict__ known, int B, int H, int W,
-                                        int* __restrict__ up, int* __restrict__ dn) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * W) return;
-  const int b = i / W, x = i % W;
+// pass 1.  grid = (ceil(W / 32), B), block = (32 columns, 32 segment slots); segment = 32 rows.
+__global__ void __launch_bounds__(1024)
+fill_column_kernel(const uint8_t* __restrict__ known, int H, int W, short* __restrict__ off) {
+  extern __shared__ int s_carry[];  // [2][nseg][32]: last valid row of the segment, first valid row
+  const int nseg = (H + 31) / 32;
+  int* s_last = s_carry;
+  int* s_first = s_carry + nseg * FILL_COLS;
+  const int b = blockIdx.y;
+  const int x = blockIdx.x * FILL_COLS + threadIdx.x;
   const uint8_t* k = known + (size_t)b * H * W;
-  int* u = up + (size_t)b * H * W;
-  int* d = dn + (size_t)b * H * W;
-  int last = -FILL_BIG;
-  for (int y = 0; y < H; ++y) {
-    if (k[(size_t)y * W + x]) last = y;
-    u[(size_t)y * W + x] = min(y - last, FILL_BIG);
+  short* o = off + (size_t)b * H * W;
+  const bool col_ok = x < W;
+  // (a) build the 32-row masks
+  for (int seg = threadIdx.y; seg < nseg; seg += blockDim.y) {
+    unsigned m = 0;
+    if (col_ok) {
+      const int y0 = seg * 32;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r)
+        if (y0 + r < H && k[(size_t)(y0 + r) * W + x]) m |= 1u << r;
+    }
+    s_last[seg * FILL_COLS + threadIdx.x] = m ? seg * 32 + 31 - __clz(m) : -1;
+    s_first[seg * FILL_COLS + threadIdx.x] = m ? seg * 32 + __ffs(m) - 1 : -1;
   }
-  int nxt = 3 * FILL_BIG;
-  for (int y = H - 1; y >= 0; --y) {
-    if (k[(size_t)y * W + x]) nxt = y;
-    d[(size_t)y * W + x] = min(nxt - y, FILL_BIG);
+  __syncthreads();
+  // (b) per column: nearest valid row strictly above / below each segment (serial over <= 256
+  //     segments, one thread per column; replaces the carries in place)
+  if (threadIdx.y == 0) {
+    int last = -1;
+    for (int seg = 0; seg < nseg; ++seg) {
+      const int mine = s_last[seg * FILL_COLS + threadIdx.x];
+      s_last[seg * FILL_COLS + threadIdx.x] = last;  // last valid row ABOVE this segment
+      if (mine >= 0) last = mine;
+    }
+    int next = -1;
+    for (int seg = nseg - 1; seg >= 0; --seg) {
+      const int mine = s_first[seg * FILL_COLS + threadIdx.x];
+      s_first[seg * FILL_COLS + threadIdx.x] = next;  // first valid row BELOW this segment
+      if (mine >= 0) next = mine;
+    }
+  }
+  __syncthreads();
+  // (c) offsets of the 32 rows of each segment (mask re-read: it is an L1/L2 hit)
+  for (int seg = threadIdx.y; seg < nseg; seg += blockDim.y) {
+    if (!col_ok) continue;
+    const int y0 = seg * 32;
+    unsigned m = 0;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r)
+      if (y0 + r < H && k[(size_t)(y0 + r) * W + x]) m |= 1u << r;
+    const int above = s_last[seg * FILL_COLS + threadIdx.x];
+    const int below = s_first[seg * FILL_COLS + threadIdx.x];
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const int y = y0 + r;
+      if (y >= H) break;
+      const unsigned lo = m & (0xFFFFFFFFu >> (31 - r));  // rows <= r of the segment
+      const unsigned hi = m >> r;                          // rows >= r
+      const int up = lo ? y - (y0 + 31 - __clz(lo)) : (above >= 0 ? y - above : INT_MAX);
+      const int dn = hi ? __ffs(hi) - 1 : (below >= 0 ? below - y : INT_MAX);
+      int v = FILL_NONE;
+      if (up != INT_MAX || dn != INT_MAX) v = up <= dn ? -up : dn;
+      o[(size_t)y * W + x] = (short)v;
+    }
   }
 }
 
-__global__ void fill_gather_kernel(const float* __restrict__ img, const int* __restrict__ up,
-                                   const int* __restrict__ dn, int B, int C, int H, int W,
-                                   long long sb, long long sc, long long sy, long long sx,
-                                   float* __restrict__ out, int* __restrict__ src_out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)B * H * W) return;
-  const int b = i / ((size_t)H * W), y = (i / W) % H, x = i % W;
-  const int* u = up + (size_t)b * H * W;
-  const int* d = dn + (size_t)b * H * W;
+// pass 2.  grid = (ceil(W / 256), H, B): a CTA owns 256 consecutive pixels of one row and stages the
+// whole row of column offsets in shared memory.
+__global__ void __launch_bounds__(256)
+fill_row_kernel(const float* __restrict__ img, const short* __restrict__ off, int C, int H, int W,
+                long long sb, long long sc, long long sy, long long sx, float* __restrict__ out,
+                int* __restrict__ src_out) {
+  extern __shared__ short s_off[];  // [W]
+  const int b = blockIdx.z, y = blockIdx.y;
+  const short* orow = off + ((size_t)b * H + y) * W;
+  for (int c = threadIdx.x; c < W; c += blockDim.x) s_off[c] = orow[c];
+  __syncthreads();
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
   long long best_d = LLONG_MAX;
   int best_r = -1, best_c = -1;
   for (int a = 0; a < W; ++a) {
@@ -55,22 +115,15 @@ __global__ void fill_gather_kernel(const float* __restrict__ img, const int* __r
       if (a == 0 && s == 1) break;
       const int c = s == 0 ? x - a : x + a;
       if (c < 0 || c >= W) continue;
-      const int uu = u[(size_t)y * W + c];
-      if (uu < FILL_BIG) {
-        const long long dd = (long long)a * a + (long long)uu * uu;
-        const int r = y - uu;
-        if (dd < best_d || (dd == best_d && (r < best_r || (r == best_r && c < best_c))))
-          best_d = dd, best_r = r, best_c = c;
-      }
-      const int dw = d[(size_t)y * W + c];
-      if (dw < FILL_BIG && dw > 0) {
-        const long long dd = (long long)a * a + (long long)dw * dw;
-        const int r = y + dw;
-        if (dd < best_d || (dd == best_d && (r < best_r || (r == best_r && c < best_c))))
-          best_d = dd, best_r = r, best_c = c;
-      }
+      const int o = s_off[c];
+      if (o == FILL_NONE) continue;
+      const long long dd = (long long)a * a + (long long)o * o;
+      const int r = y + o;
+      if (dd < best_d || (dd == best_d && (r < best_r || (r == best_r && c < best_c))))
+        best_d = dd, best_r = r, best_c = c;
     }
   }
+  const size_t i = ((size_t)b * H + y) * W + x;
   if (src_out) src_out[i] = best_r < 0 ? -1 : best_r * W + best_c;
   const long long ob = (long long)b * sb + (long long)y * sy + (long long)x * sx;
   for (int ch = 0; ch < C; ++ch) {
@@ -81,26 +134,29 @@ __global__ void fill_gather_kernel(const float* __restrict__ img, const int* __r
 }
 
 size_t nearest_fill_workspace_bytes(int B, int H, int W) {
-  return (size_t)B * H * W * 2 * sizeof(int) + 256;
+  return (size_t)B * H * W * sizeof(short) + 256;
 }
 
 int nearest_fill_launch(const float* img, const uint8_t* known, int B, int C, int H, int W,
                         int channels_last, void* workspace, float* out, int* src_index,
                         cudaStream_t stream) {
   PDR_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "empty image");
+  PDR_CHECK_ARG(H <= FILL_MAX_H && W <= 16384, "nearest fill: image larger than %d x 16384",
+                FILL_MAX_H);
   PDR_CHECK_ARG(img != out, "nearest fill cannot run in place");
-  int* up = (int*)workspace;
-  int* dn = up + (size_t)B * H * W;
+  short* off = (short*)workspace;
   long long sb = (long long)C * H * W, sc, sy, sx;
   if (channels_last) {
     sc = 1, sx = C, sy = (long long)W * C;
   } else {
     sc = (long long)H * W, sy = W, sx = 1;
   }
-  fill_column_scan_kernel<<<cdiv((long long)B * W, 128), 128, 0, stream>>>(known, B, H, W, up, dn);
+  const int nseg = (H + 31) / 32;
+  fill_column_kernel<<<dim3(cdiv(W, FILL_COLS), B), dim3(FILL_COLS, 32),
+                       2 * nseg * FILL_COLS * sizeof(int), stream>>>(known, H, W, off);
   PDR_COUNT_LAUNCH();
-  fill_gather_kernel<<<cdiv((long long)B * H * W, 256), 256, 0, stream>>>(
-      img, up, dn, B, C, H, W, sb, sc, sy, sx, out, src_index);
+  fill_row_kernel<<<dim3(cdiv(W, 256), H, B), 256, W * sizeof(short), stream>>>(
+      img, off, C, H, W, sb, sc, sy, sx, out, src_index);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;

@@ -136,105 +136,272 @@ int project_launch(const float* cams, const float* vertices, int Vm, const float
 }
 
 // ------------------------------------------------------------------ K2 ----
-// (SUBPIX, snap_coord, edge_inclusive, floordiv: geom_common.cuh)
+// Tile-binned z-buffer rasteriser (SUBPIX, snap_coord, edge_inclusive, floordiv: geom_common.cuh).
+//
+//   raster_setup_kernel   thread per (view, triangle): snap the vertices to the 1/256-px grid, store a
+//                         64-byte record, count the 32 x 8 pixel tiles its bounding box overlaps
+//                         (triangles spanning more than RT_MAX_SPAN tiles go to a per-view list);
+//   raster_scan_kernel    exclusive scan of the per-tile counts (one block);
+//   raster_bin_kernel     thread per (view, triangle): write the face id into the bins of its tiles;
+//   raster_tile_kernel    one CTA per tile, one THREAD PER PIXEL: the tile's triangle records are
+//                         staged through shared memory in chunks and every thread walks them,
+//                         keeping min (z, face id) in a register - no atomics, no z-buffer in global
+//                         memory - then writes depth / face id / masks (and the res/2 "any" mask of
+//                         demo.py:103-104) directly.
+// The result is the minimum over a SET of (z, id) keys, so the (non-deterministic) order of the
+// faces inside a bin does not matter: output is bit-identical to the one-warp-per-triangle +
+// atomicMin version it replaces, and to oracle/project.py:rasterize.
+static constexpr int RT_W = 32, RT_H = 8;   // pixel tile of one CTA
+static constexpr int RT_MAX_SPAN = 16;      // more tiles than this: the per-view "large" list
+static constexpr int RT_CHUNK = 64;         // triangle records staged per round
 
-__global__ void zkey_init_kernel(unsigned long long* keys, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keys[i] = ~0ull;
+struct __align__(16) RasterTri {
+  long long ax, ay, bx, by, cx, cy;  // snapped vertices, 1/256 px
+  float az, bz, cz;
+  int f;
+};
+static_assert(sizeof(RasterTri) == 64, "RasterTri must be 64 bytes");
+
+struct RasterWs {
+  RasterTri* tris;     // [V*F]
+  int* counts;         // [V*T + 1]  per-tile counts, then write cursors
+  int* offs;           // [V*T + 1]  exclusive scan
+  int* bins;           // [V*F*RT_MAX_SPAN]
+  int* large;          // [V*F]
+  int* large_count;    // [V]
+};
+
+__host__ __device__ inline size_t rt_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static RasterWs raster_ws_carve(void* ws, int V, int F, int tiles) {
+  uint8_t* w = (uint8_t*)ws;
+  RasterWs r;
+  r.tris = (RasterTri*)w;
+  w += rt_align((size_t)V * F * sizeof(RasterTri));
+  r.counts = (int*)w;
+  w += rt_align(((size_t)V * tiles + 1) * 4);
+  r.large_count = (int*)w;  // directly after counts: one memset clears both
+  w += rt_align((size_t)V * 4);
+  r.offs = (int*)w;
+  w += rt_align(((size_t)V * tiles + 1) * 4);
+  r.bins = (int*)w;
+  w += rt_align((size_t)V * F * RT_MAX_SPAN * 4);
+  r.large = (int*)w;
+  return r;
 }
 
-// one warp per (view, triangle); lanes stride over the bounding box
-__global__ void raster_kernel(const float* __restrict__ pos, const int* __restrict__ faces, int V,
-                              int Vm, int F, int res, unsigned long long* __restrict__ keys) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= V * F) return;
-  const int v = warp / F, f = warp - v * F;
-  const int ia = faces[3 * f], ib = faces[3 * f + 1], ic = faces[3 * f + 2];
-  const float4* P = reinterpret_cast<const float4*>(pos) + (size_t)v * Vm;
-  const float4 A = P[ia], B = P[ib], C = P[ic];
-  const long long ax = snap_coord(A.x, res), ay = snap_coord(A.y, res);
-  const long long bx = snap_coord(B.x, res), by = snap_coord(B.y, res);
-  const long long cx = snap_coord(C.x, res), cy = snap_coord(C.y, res);
-  const long long area = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
-  if (area == 0) return;
-  const long long sgn = area > 0 ? 1 : -1;
+size_t rasterize_workspace_bytes(int V, int F, int res) {
+  const size_t tiles = (size_t)cdiv(res, RT_W) * cdiv(res, RT_H);
+  return rt_align((size_t)V * F * sizeof(RasterTri)) + 2 * rt_align(((size_t)V * tiles + 1) * 4) +
+         rt_align((size_t)V * 4) + rt_align((size_t)V * F * RT_MAX_SPAN * 4) +
+         rt_align((size_t)V * F * 4) + 256;
+}
+
+// pixel bounding box of a snapped triangle clipped to the image; false when empty / degenerate
+__device__ __forceinline__ bool raster_bbox(const RasterTri& t, int res, int& x0, int& y0, int& x1,
+                                            int& y1) {
+  const long long area = (t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax);
+  if (area == 0) return false;
   const long long H = SUBPIX / 2;
-  long long xmin = floordiv(min(ax, min(bx, cx)) - H + SUBPIX - 1, SUBPIX);
-  long long xmax = floordiv(max(ax, max(bx, cx)) - H, SUBPIX);
-  long long ymin = floordiv(min(ay, min(by, cy)) - H + SUBPIX - 1, SUBPIX);
-  long long ymax = floordiv(max(ay, max(by, cy)) - H, SUBPIX);
+  long long xmin = floordiv(min(t.ax, min(t.bx, t.cx)) - H + SUBPIX - 1, SUBPIX);
+  long long xmax = floordiv(max(t.ax, max(t.bx, t.cx)) - H, SUBPIX);
+  long long ymin = floordiv(min(t.ay, min(t.by, t.cy)) - H + SUBPIX - 1, SUBPIX);
+  long long ymax = floordiv(max(t.ay, max(t.by, t.cy)) - H, SUBPIX);
   xmin = max(xmin, 0ll);
   ymin = max(ymin, 0ll);
   xmax = min(xmax, (long long)res - 1);
   ymax = min(ymax, (long long)res - 1);
-  if (xmin > xmax || ymin > ymax) return;
-  const bool incA = edge_inclusive(sgn * (cx - bx), sgn * (cy - by));
-  const bool incB = edge_inclusive(sgn * (ax - cx), sgn * (ay - cy));
-  const bool incC = edge_inclusive(sgn * (bx - ax), sgn * (by - ay));
-  const int bw = (int)(xmax - xmin + 1);
-  const long long npx = (long long)bw * (ymax - ymin + 1);
-  unsigned long long* kv = keys + (size_t)v * res * res;
-  for (long long t = lane; t < npx; t += 32) {
-    const long long yy = ymin + t / bw, xx = xmin + t % bw;
-    const long long px = xx * SUBPIX + H, py = yy * SUBPIX + H;
-    const long long eA = sgn * ((cx - bx) * (py - by) - (cy - by) * (px - bx));
-    const long long eB = sgn * ((ax - cx) * (py - cy) - (ay - cy) * (px - cx));
-    const long long eC = sgn * ((bx - ax) * (py - ay) - (by - ay) * (px - ax));
-    const bool in = (eA > 0 || (eA == 0 && incA)) && (eB > 0 || (eB == 0 && incB)) &&
-                    (eC > 0 || (eC == 0 && incC));
-    if (!in) continue;
-    const float wa = __ll2float_rn(eA), wb = __ll2float_rn(eB), wc = __ll2float_rn(eC);
-    const float tot = __ll2float_rn(eA + eB + eC);
-    const float z = ((wa * A.z + wb * B.z) + wc * C.z) / tot;
-    if (!(z >= -1.0f && z <= 1.0f)) continue;
-    const unsigned long long key =
-        ((unsigned long long)float_to_ordered_u32(z) << 32) | (unsigned int)f;
-    atomicMin(&kv[yy * res + xx], key);
+  if (xmin > xmax || ymin > ymax) return false;
+  x0 = (int)xmin, x1 = (int)xmax, y0 = (int)ymin, y1 = (int)ymax;
+  return true;
+}
+
+__global__ void raster_setup_kernel(const float* __restrict__ pos, const int* __restrict__ faces,
+                                    int V, int Vm, int F, int res, int tiles_x, int tiles,
+                                    RasterWs ws) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V * F) return;
+  const int v = i / F, f = i - v * F;
+  const int ia = faces[3 * f], ib = faces[3 * f + 1], ic = faces[3 * f + 2];
+  const float4* P = reinterpret_cast<const float4*>(pos) + (size_t)v * Vm;
+  const float4 A = P[ia], B = P[ib], C = P[ic];
+  RasterTri t;
+  t.ax = snap_coord(A.x, res), t.ay = snap_coord(A.y, res);
+  t.bx = snap_coord(B.x, res), t.by = snap_coord(B.y, res);
+  t.cx = snap_coord(C.x, res), t.cy = snap_coord(C.y, res);
+  t.az = A.z, t.bz = B.z, t.cz = C.z;
+  t.f = f;
+  ws.tris[i] = t;
+  int x0, y0, x1, y1;
+  if (!raster_bbox(t, res, x0, y0, x1, y1)) return;
+  const int tx0 = x0 / RT_W, tx1 = x1 / RT_W, ty0 = y0 / RT_H, ty1 = y1 / RT_H;
+  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > RT_MAX_SPAN) {
+    ws.large[(size_t)v * F + atomicAdd(&ws.large_count[v], 1)] = f;
+    return;
+  }
+  for (int ty = ty0; ty <= ty1; ++ty)
+    for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&ws.counts[(size_t)v * tiles + ty * tiles_x + tx], 1);
+}
+
+// exclusive scan of counts[0..n) into offs[0..n], single block; counts are zeroed (they become
+// the write cursors of raster_bin_kernel)
+__global__ void raster_scan_kernel(int* __restrict__ counts, int* __restrict__ offs, int n) {
+  __shared__ int s[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int val = i < n ? counts[i] : 0;
+    s[threadIdx.x] = val;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int t = threadIdx.x >= o ? s[threadIdx.x - o] : 0;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < n) {
+      offs[i] = carry + s[threadIdx.x] - val;
+      counts[i] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += s[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offs[n] = carry;
+}
+
+__global__ void raster_bin_kernel(int V, int F, int res, int tiles_x, int tiles, RasterWs ws) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= V * F) return;
+  const int v = i / F, f = i - v * F;
+  const RasterTri t = ws.tris[i];
+  int x0, y0, x1, y1;
+  if (!raster_bbox(t, res, x0, y0, x1, y1)) return;
+  const int tx0 = x0 / RT_W, tx1 = x1 / RT_W, ty0 = y0 / RT_H, ty1 = y1 / RT_H;
+  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > RT_MAX_SPAN) return;
+  for (int ty = ty0; ty <= ty1; ++ty)
+    for (int tx = tx0; tx <= tx1; ++tx) {
+      const size_t tile = (size_t)v * tiles + ty * tiles_x + tx;
+      ws.bins[ws.offs[tile] + atomicAdd(&ws.counts[tile], 1)] = f;
+    }
+}
+
+// coverage + depth of pixel centre (px, py) (sub-pixel units) for one triangle record
+__device__ __forceinline__ void raster_shade(const RasterTri& t, long long px, long long py,
+                                             unsigned long long& best) {
+  const long long area = (t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax);
+  const long long sgn = area > 0 ? 1 : -1;
+  const long long eA = sgn * ((t.cx - t.bx) * (py - t.by) - (t.cy - t.by) * (px - t.bx));
+  const long long eB = sgn * ((t.ax - t.cx) * (py - t.cy) - (t.ay - t.cy) * (px - t.cx));
+  const long long eC = sgn * ((t.bx - t.ax) * (py - t.ay) - (t.by - t.ay) * (px - t.ax));
+  if (eA < 0 || eB < 0 || eC < 0) return;
+  if ((eA == 0 && !edge_inclusive(sgn * (t.cx - t.bx), sgn * (t.cy - t.by))) ||
+      (eB == 0 && !edge_inclusive(sgn * (t.ax - t.cx), sgn * (t.ay - t.cy))) ||
+      (eC == 0 && !edge_inclusive(sgn * (t.bx - t.ax), sgn * (t.by - t.ay))))
+    return;
+  const float wa = __ll2float_rn(eA), wb = __ll2float_rn(eB), wc = __ll2float_rn(eC);
+  const float tot = __ll2float_rn(eA + eB + eC);
+  const float z = ((wa * t.az + wb * t.bz) + wc * t.cz) / tot;
+  if (!(z >= -1.0f && z <= 1.0f)) return;
+  const unsigned long long key =
+      ((unsigned long long)float_to_ordered_u32(z) << 32) | (unsigned int)t.f;
+  best = min(best, key);
+}
+
+__global__ void __launch_bounds__(RT_W * RT_H)
+raster_tile_kernel(int V, int F, int res, int out_res, int tiles_x, int tiles, RasterWs ws,
+                   float* __restrict__ depth, long long* __restrict__ face_idx,
+                   uint8_t* __restrict__ mask_cam, uint8_t* __restrict__ mask_out) {
+  __shared__ RasterTri st[RT_CHUNK];
+  __shared__ int s_n;
+  __shared__ uint8_t s_hit[RT_H][RT_W];
+  const int tile = blockIdx.x % tiles, v = blockIdx.x / tiles;
+  const int tx = tile % tiles_x, ty = tile / tiles_x;
+  const int lx = threadIdx.x % RT_W, ly = threadIdx.x / RT_W;
+  const int x = tx * RT_W + lx, y = ty * RT_H + ly;
+  const bool inside = x < res && y < res;
+  const long long px = (long long)x * SUBPIX + SUBPIX / 2, py = (long long)y * SUBPIX + SUBPIX / 2;
+  unsigned long long best = ~0ull;
+  const RasterTri* tris = ws.tris + (size_t)v * F;
+  // ---- the tile's bin ----
+  const int b0 = ws.offs[(size_t)v * tiles + tile], b1 = ws.offs[(size_t)v * tiles + tile + 1];
+  for (int base = b0; base < b1; base += RT_CHUNK) {
+    const int n = min(RT_CHUNK, b1 - base);
+    __syncthreads();
+    // 4 threads copy one 64-byte record (16 bytes each)
+    for (int k = threadIdx.x; k < n * 4; k += RT_W * RT_H) {
+      const int r = k >> 2, part = k & 3;
+      reinterpret_cast<uint4*>(&st[r])[part] =
+          reinterpret_cast<const uint4*>(&tris[ws.bins[base + r]])[part];
+    }
+    __syncthreads();
+    if (inside)
+      for (int r = 0; r < n; ++r) raster_shade(st[r], px, py, best);
+  }
+  // ---- the view's large triangles (bounding box > RT_MAX_SPAN tiles), filtered per tile ----
+  const int nl = ws.large_count[v];
+  const int* large = ws.large + (size_t)v * F;
+  const int X0 = tx * RT_W, X1 = min(X0 + RT_W, res) - 1, Y0 = ty * RT_H, Y1 = min(Y0 + RT_H, res) - 1;
+  for (int base = 0; base < nl; base += RT_CHUNK) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if (threadIdx.x < RT_CHUNK && base + threadIdx.x < nl) {
+      const RasterTri t = tris[large[base + threadIdx.x]];
+      int x0, y0, x1, y1;
+      if (raster_bbox(t, res, x0, y0, x1, y1) && x0 <= X1 && x1 >= X0 && y0 <= Y1 && y1 >= Y0)
+        st[atomicAdd(&s_n, 1)] = t;
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (inside)
+      for (int r = 0; r < n; ++r) raster_shade(st[r], px, py, best);
+  }
+  const bool hit = inside && best != ~0ull;
+  if (inside) {
+    const size_t p = ((size_t)v * res + y) * res + x;
+    depth[p] = hit ? ordered_u32_to_float((unsigned int)(best >> 32)) : 0.0f;
+    face_idx[p] = hit ? (long long)(unsigned int)(best & 0xFFFFFFFFu) : -1ll;
+    mask_cam[p] = hit ? 1 : 0;
+  }
+  if (out_res == res) {
+    if (inside) mask_out[((size_t)v * res + y) * res + x] = hit ? 1 : 0;
+  } else {  // res == 2 * out_res: OR of each 2 x 2 block (RT_W, RT_H are even, so blocks stay in the tile)
+    s_hit[ly][lx] = hit ? 1 : 0;
+    __syncthreads();
+    if (ly < RT_H / 2 && lx < RT_W / 2) {
+      const int ox = tx * (RT_W / 2) + lx, oy = ty * (RT_H / 2) + ly;
+      if (ox < out_res && oy < out_res)
+        mask_out[((size_t)v * out_res + oy) * out_res + ox] =
+            s_hit[2 * ly][2 * lx] | s_hit[2 * ly][2 * lx + 1] | s_hit[2 * ly + 1][2 * lx] |
+            s_hit[2 * ly + 1][2 * lx + 1];
+    }
   }
 }
 
-// keys -> depth / face id / mask (+ the res-sized "any" mask, demo.py:103-104)
-__global__ void raster_resolve_kernel(const unsigned long long* __restrict__ keys, int V, int res,
-                                      int out_res, float* __restrict__ depth,
-                                      long long* __restrict__ face_idx,
-                                      uint8_t* __restrict__ mask_cam,
-                                      uint8_t* __restrict__ mask_out) {
-  // thread per OUTPUT pixel of the (possibly half-resolution) mask; ratio = res / out_res (1 or 2)
-  const int ratio = res / out_res;
-  const size_t n = (size_t)V * out_res * out_res;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int ox = i % out_res, oy = (i / out_res) % out_res, v = i / ((size_t)out_res * out_res);
-  bool any = false;
-  for (int dy = 0; dy < ratio; ++dy)
-    for (int dx = 0; dx < ratio; ++dx) {
-      const size_t p = ((size_t)v * res + (oy * ratio + dy)) * res + (ox * ratio + dx);
-      const unsigned long long k = keys[p];
-      const bool hit = k != ~0ull;
-      depth[p] = hit ? ordered_u32_to_float((unsigned int)(k >> 32)) : 0.0f;
-      face_idx[p] = hit ? (long long)(unsigned int)(k & 0xFFFFFFFFu) : -1ll;
-      mask_cam[p] = hit ? 1 : 0;
-      any |= hit;
-    }
-  mask_out[i] = any ? 1 : 0;
-}
-
 int rasterize_launch(const float* pos, const int* faces, int V, int Vm, int F, int res,
-                     int out_res, unsigned long long* ws_keys, float* depth, long long* face_idx,
+                     int out_res, void* workspace, float* depth, long long* face_idx,
                      uint8_t* mask_cam, uint8_t* mask_out, cudaStream_t stream) {
   PDR_CHECK_ARG(out_res == res || out_res * 2 == res,
                 "mask resize %d -> %d unsupported (cam_res must equal res or 2*res)", res, out_res);
   PDR_CHECK_ARG(F > 0 && V > 0, "empty mesh");
-  const size_t n = (size_t)V * res * res;
-  zkey_init_kernel<<<cdiv(n, 256), 256, 0, stream>>>(ws_keys, n);
+  PDR_CHECK_ARG(((uintptr_t)workspace & 15) == 0, "rasterize workspace must be 16-byte aligned");
+  const int tiles_x = cdiv(res, RT_W), tiles_y = cdiv(res, RT_H), tiles = tiles_x * tiles_y;
+  PDR_CHECK_ARG((long long)V * tiles < (1ll << 30), "raster grid too large");
+  RasterWs ws = raster_ws_carve(workspace, V, F, tiles);
+  // counts and large_count are adjacent: one memset
+  PDR_CUDA(cudaMemsetAsync(ws.counts, 0, (uint8_t*)ws.offs - (uint8_t*)ws.counts, stream));
+  raster_setup_kernel<<<cdiv((long long)V * F, 256), 256, 0, stream>>>(pos, faces, V, Vm, F, res,
+                                                                      tiles_x, tiles, ws);
   PDR_COUNT_LAUNCH();
-  const long long warps = (long long)V * F;
-  raster_kernel<<<cdiv(warps * 32, 256), 256, 0, stream>>>(pos, faces, V, Vm, F, res, ws_keys);
+  raster_scan_kernel<<<1, 1024, 0, stream>>>(ws.counts, ws.offs, V * tiles);
   PDR_COUNT_LAUNCH();
-  const size_t no = (size_t)V * out_res * out_res;
-  raster_resolve_kernel<<<cdiv(no, 256), 256, 0, stream>>>(ws_keys, V, res, out_res, depth,
-                                                          face_idx, mask_cam, mask_out);
+  raster_bin_kernel<<<cdiv((long long)V * F, 256), 256, 0, stream>>>(V, F, res, tiles_x, tiles, ws);
+  PDR_COUNT_LAUNCH();
+  raster_tile_kernel<<<V * tiles, RT_W * RT_H, 0, stream>>>(V, F, res, out_res, tiles_x, tiles, ws,
+                                                           depth, face_idx, mask_cam, mask_out);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;

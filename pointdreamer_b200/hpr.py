@@ -41,4 +41,4 @@ def hidden_point_removal(points, eye_positions, radius):
     vis = torch.empty(V, N, dtype=torch.uint8, device=dev)
     _lib.call("pdr_hidden_point_removal", pts, N, V, frames, ctypes.c_double(float(radius)), ws,
               vis)
-    return vis.bool()
+    return vis.view(torch.bool)

@@ -14,7 +14,18 @@ from . import camera as _camera
 
 
 def _u8(t):
-    return t.to(torch.uint8) if t.dtype != torch.uint8 else t
+    """Masks cross the ABI as u8.  torch.bool has the same 1-byte storage holding 0/1, so a bool
+    tensor is reinterpreted in place (no conversion kernel); other dtypes are converted."""
+    if t.dtype == torch.uint8:
+        return t
+    if t.dtype == torch.bool:
+        return t.view(torch.uint8)
+    return t.to(torch.uint8)
+
+
+def _as_bool(t):
+    """u8 0/1 tensor written by a kernel -> the reference's bool dtype, zero copy."""
+    return t.view(torch.bool)
 
 
 def get_rendered_hard_mask_and_face_idx_batch(cams, vertices, faces, points, glctx=None,
@@ -59,15 +70,17 @@ def rasterize(pos, faces, res, out_res):
     V, Vm = pos.shape[0], pos.shape[1]
     f32 = faces.to(torch.int32).contiguous()
     F = f32.shape[0]
-    keys = torch.empty(V * res * res, dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    lib.pdr_rasterize_workspace_bytes.restype = ctypes.c_size_t
+    ws = torch.empty(lib.pdr_rasterize_workspace_bytes(V, F, res), dtype=torch.uint8, device=dev)
     depth = torch.empty(V, res, res, device=dev)
     face_idx = torch.empty(V, res, res, dtype=torch.int64, device=dev)
     mask_cam = torch.empty(V, res, res, dtype=torch.uint8, device=dev)
     mask_out = torch.empty(V, out_res, out_res, dtype=torch.uint8, device=dev)
     _lib.call("pdr_rasterize", pos.contiguous(), f32, V, Vm, F, res, out_res,
-              keys, depth, face_idx, mask_cam,
+              ws, depth, face_idx, mask_cam,
               mask_out)
-    return mask_cam.bool(), face_idx, depth, mask_out.bool()
+    return _as_bool(mask_cam), face_idx, depth, _as_bool(mask_out)
 
 
 def resize_hard_masks(hard_masks, res):
@@ -80,7 +93,7 @@ def resize_hard_masks(hard_masks, res):
         raise NotImplementedError("cam_res must equal res or 2*res")
     out = torch.empty(V, res, res, dtype=torch.uint8, device=hard_masks.device)
     _lib.call("pdr_mask_half_any", _u8(hard_masks).contiguous(), V, H, out)
-    return out.bool()
+    return _as_bool(out)
 
 
 def get_point_validation_by_depth(cam_res, point_uvs, point_depths, mesh_depths, offset=0,
@@ -94,7 +107,7 @@ def get_point_validation_by_depth(cam_res, point_uvs, point_depths, mesh_depths,
               point_depths.contiguous(), mesh_depths.contiguous(), V, N,
               int(cam_res), float(offset), int(cam_res), visib, pix,
               None)
-    return visib.bool(), pix
+    return _as_bool(visib), pix
 
 
 def get_point_pixels(point_uvs, res):
@@ -197,7 +210,7 @@ def interpolate(attr, pos, faces, face_idx, attr_faces, flip_y=False, want_mask=
     _lib.call("pdr_interpolate", pos.contiguous(), faces.to(torch.int32).contiguous(),
               face_idx.contiguous(), attr.float().contiguous(),
               attr_faces.to(torch.int32).contiguous(), V, Vm, res, C, 1 if flip_y else 0, out, mask)
-    return (out, mask.bool()) if want_mask else out
+    return (out, _as_bool(mask)) if want_mask else out
 
 
 def face_normals(vertices, faces):

@@ -70,7 +70,7 @@ def unproject(inpainted_images, vertices, f_normals, view_img_res, cams, cam_res
               1 if complete_unseen_by_projection else 0, ws, atlas,
               shr, view_ids, coords, points,
               painted)
-    return atlas, shr.bool(), view_ids, coords, points, painted.bool()
+    return atlas, shr.view(torch.bool), view_ids, coords, points, painted.view(torch.bool)
 
 
 def count_texels(mask):

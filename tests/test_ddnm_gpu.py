@@ -114,7 +114,9 @@ def test_chain_small_vs_oracle(cuda):
     mse = float(((out - ref) ** 2).mean())
     psnr = 10 * np.log10(1.0 / max(mse, 1e-20))
     print(f"chain vs oracle: max abs {err.max():.3e}, mean abs {err.mean():.3e}, PSNR {psnr:.1f} dB")
-    assert err.mean() < 2e-3 and psnr > 45
+    # observed on B200: max abs 2.56e-2 (a 10-step chain of a toy model amplifies fp16 rounding),
+    # mean abs 5.5e-5, PSNR 62.4 dB; bounds = 1.5 x observed
+    assert err.max() < 3.9e-2 and err.mean() < 8.3e-5 and psnr > 60.5
     # serial single-view calls reproduce the batched result chain by chain
     inp2 = Inpainter(cuda, state_dict=sd, model_config=SMALL, ddnm_config=cfg, seed=42, offset=0)
     for v in range(V):

@@ -63,10 +63,12 @@ def test_default_yaml_flow_matches_oracle(cuda):
     psnr = 10 * np.log10(1.0 / max(mse, 1e-30))
     print(f"default.yaml flow vs oracle: max abs {err.max():.3e}, PSNR {psnr:.1f} dB, "
           f"texels off by >1e-3: {(err.max(-1) > 1e-3).mean():.2e}")
-    assert psnr > 55.0
-    assert (err.max(-1) > 1e-3).mean() < 5e-3
+    # observed on B200: max abs 2.5e-3, PSNR 88.3 dB, 2.6e-4 of the texels beyond 1e-3 (the L1 loss has a
+    # sign() in its gradient: rounding-level differences flip signs where render == target)
+    assert err.max() < 3.8e-3 and psnr > 86.0
+    assert (err.max(-1) > 1e-3).mean() < 3.9e-4
     # the metric of BASELINE.json: texture PSNR on the 8-bit atlas image (psnr_ssmi.py:23-42)
     from pointdreamer_b200 import metrics
     p8 = metrics.calculate_psnr(metrics.atlas_to_uint8(atlas), metrics.atlas_to_uint8(ref))
     print(f"8-bit texture PSNR, CUDA flow vs oracle flow: {p8:.1f} dB")
-    assert p8 > 50.0
+    assert p8 > 70.0  # observed 72.0 dB

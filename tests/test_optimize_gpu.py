@@ -127,8 +127,9 @@ def test_optimize_color_100_iterations_vs_oracle(cuda, golden, vis):
           f"texels off by >1e-3: {(err > 1e-3).mean():.2e}")
     # the L1 loss has a sign() in its gradient: an fp64-rounding-level difference can flip a sign
     # where render == target, so a few texels may drift by a fraction of one lr step
-    assert psnr > 60.0
-    assert (err > 1e-3).mean() < 1e-3
+    # observed on B200: max abs 5.1e-3 / 6.9e-3, PSNR 82.4 / 82.7 dB, 8.0e-4 / 7.6e-4 beyond 1e-3
+    assert err.max() < 1.05e-2 and psnr > 80.5
+    assert (err > 1e-3).mean() < 1.2e-3
     assert np.abs(images.cpu().numpy() - img_o).max() < 2e-2
 
 

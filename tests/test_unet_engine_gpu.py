@@ -32,8 +32,10 @@ def test_engine_small_vs_reference_golden(cuda):
     rel = np.linalg.norm(y - o16) / np.linalg.norm(o16)
     print(f"engine vs fp16-emulating oracle: max abs {e_or:.3e}, rel L2 {rel:.3e}; "
           f"vs reference fp32: max abs {e_ref:.3e} (oracle16 vs ref32 {np.abs(o16 - ref32).max():.3e})")
-    assert e_or < 6e-3 and rel < 2e-3
-    assert e_ref < 1e-2
+    # observed on B200: max abs 1.53e-3 / rel L2 1.16e-3 vs the fp16-emulating oracle, 1.56e-3 vs the
+    # reference's fp32 output (the oracle's own fp16-vs-fp32 gap is 1.77e-3); bounds = 1.5 x observed
+    assert e_or < 2.3e-3 and rel < 1.75e-3
+    assert e_ref < 2.35e-3
     # 3-channel mode (what the sampler consumes) equals the first 3 channels
     y3 = eng.forward(x, t, n_out=3).cpu().numpy()
     assert np.array_equal(y3, y[:, :3])
@@ -62,7 +64,8 @@ def test_engine_medium_vs_oracle(cuda):
     rel = np.linalg.norm(y - o16) / np.linalg.norm(o16)
     print(f"medium: engine vs oracle16 max abs {np.abs(y - o16).max():.3e} rel L2 {rel:.3e}; "
           f"engine vs oracle32 {np.abs(y - o32).max():.3e}; oracle16 vs oracle32 {np.abs(o16 - o32).max():.3e}")
-    assert rel < 2e-3 and np.abs(y - o16).max() < 1e-2
+    # observed: max abs 1.28e-3, rel L2 8.0e-4 (oracle16 vs oracle32: 1.46e-3)
+    assert rel < 1.2e-3 and np.abs(y - o16).max() < 1.95e-3
     y1 = eng(x[1:2].to(cuda), t[1:2].to(cuda)).cpu().numpy()
     assert np.array_equal(y1[0], y[1])  # batch-invariant bits
 
@@ -106,7 +109,8 @@ def test_engine_full_size_vs_oracle(cuda):
     print(f"full model: engine vs oracle16 max abs {np.abs(y - o16).max():.3e}, rel L2 {rel:.3e}, "
           f"out std {o16.std():.3f}")
     assert np.isfinite(y).all()
-    assert rel < 3e-3 and np.abs(y - o16).max() < 2e-2
+    # observed: max abs 1.14e-3, rel L2 7.4e-4 on an output of std 0.29
+    assert rel < 1.1e-3 and np.abs(y - o16).max() < 1.75e-3
 
 
 def test_fused_groupnorm_equals_separate_pass_bitwise(cuda):
