@@ -605,6 +605,9 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other_configs short runs")
     ap.add_argument("--shapes-per-gpu", type=int, default=None, help="override S of the config")
+    ap.add_argument("--views", type=int, default=None,
+                    help="override view_num of the config (profiling the geometry kernels at 8 views "
+                         "without the diffusion: --config 0 --views 8)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -626,6 +629,10 @@ def main():
     _lib.load()
     if args.shapes_per_gpu:
         CONFIGS[args.config] = dict(CONFIGS[args.config], S=args.shapes_per_gpu)
+    if args.views:
+        c0 = CONFIGS[args.config]
+        CONFIGS[args.config] = dict(c0, V=args.views,
+                                    workload=c0["workload"] + f" [view_num overridden to {args.views}]")
 
     b = Bench(args, args.config, rank, local_rank, world, dev, shard=args.shard, flow=args.flow)
     r = b.run(args.steps, args.warmup)

@@ -17,7 +17,9 @@
 //     unet.py:660-662) so the concat is never materialised.
 //
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..7 = epilogue (TMEM -> registers -> +bias (+residual) -> fp16 -> global).
+// warps 4..7 = epilogue (TMEM -> registers -> +bias (+residual) -> fp16 -> global).  The halo kernel
+// has two TMA producers (warp 0: weight tiles, warp 3: halo tiles) and 8 more warps that apply a
+// fused GroupNorm to the halo tile in shared memory.
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -743,19 +745,51 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===================================================== TMA producer ====
+    // ======================================= TMA producer: weight tiles (B) ====
+    // The two rings have their own producers: were the halo (A) loads issued by this loop too,
+    // between the tap loads, the halo of chunk c+1 could only be requested once every tap of
+    // chunk c had a free slot, i.e. ONE chunk ahead of the MMAs whatever the depth of the A
+    // ring - too late when the transform warps still have to activate the tile (fused GroupNorm).
     if (elect_one_sync()) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+      int bs = 0;
+      uint32_t bph = 0;
       for (int work = worker; work < num_work; work += num_workers) {
         const int n_tile = work % args.tiles_n;
+        const int n0 = n_tile * BN + (TWO ? (int)rank * 128 : 0);
+        for (int ch = 0; ch < chunks_all; ++ch) {
+          const bool main_chunk = ch < chunks_main;
+          const int ntaps = main_chunk ? 9 : 1;
+          for (int t = 0; t < ntaps; ++t) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            uint8_t* sb = smem + L::B_OFFSET + bs * L::B_BYTES;
+            if (leader) mbar_expect_tx(&b_full[bs], TXMUL * L::B_BYTES);
+            const int kcoord = main_chunk ? t * Ctot + ch * BLOCK_K
+                                          : 9 * Ctot + (ch - chunks_main) * BLOCK_K;
+            if (TWO)
+              tma2_load_2d(sb, &tmB, &b_full[bs], kcoord, n0);
+            else
+              tma_load_2d(sb, &tmB, &b_full[bs], kcoord, n0);
+            if (++bs == BST) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // ========================================= TMA producer: halo tiles (A) ====
+    if (elect_one_sync()) {
+      int as = 0;
+      uint32_t aph = 0;
+      for (int work = worker; work < num_work; work += num_workers) {
         int m_tile = TWO ? (work / args.tiles_n) * 2 + (int)rank : work / args.tiles_n;
         const int tx = m_tile % args.tiles_x;
         m_tile /= args.tiles_x;
         const int ty = m_tile % args.tiles_y;
         const int tb = m_tile / args.tiles_y;
         const int x0 = tx * 8 - 1, y0 = ty * 16 - 1;  // halo origin (may be -1: zero fill)
-        const int n0 = n_tile * BN + (TWO ? (int)rank * 128 : 0);
         for (int ch = 0; ch < chunks_all; ++ch) {
           const bool main_chunk = ch < chunks_main;
           mbar_wait(&a_empty[as], aph ^ 1);
@@ -780,22 +814,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           if (++as == AST) {
             as = 0;
             aph ^= 1;
-          }
-          const int ntaps = main_chunk ? 9 : 1;
-          for (int t = 0; t < ntaps; ++t) {
-            mbar_wait(&b_empty[bs], bph ^ 1);
-            uint8_t* sb = smem + L::B_OFFSET + bs * L::B_BYTES;
-            if (leader) mbar_expect_tx(&b_full[bs], TXMUL * L::B_BYTES);
-            const int kcoord = main_chunk ? t * Ctot + ch * BLOCK_K
-                                          : 9 * Ctot + (ch - chunks_main) * BLOCK_K;
-            if (TWO)
-              tma2_load_2d(sb, &tmB, &b_full[bs], kcoord, n0);
-            else
-              tma_load_2d(sb, &tmB, &b_full[bs], kcoord, n0);
-            if (++bs == BST) {
-              bs = 0;
-              bph ^= 1;
-            }
           }
         }
       }

@@ -233,26 +233,32 @@ hpr_compact_c_kernel(int N, int stride, int offset, HprWs ws, uint8_t* __restric
   if (threadIdx.x == 0) ws.nC[v] = base;
 }
 
-// tighten [lo, hi] on the line p0 + t d with one earlier constraint; divisions only when the bound
-// actually moves (rare), comparisons by cross-multiplication otherwise
-__device__ __forceinline__ void hpr_clip(const double4 c, double uL, double vL, double wL,
+// tighten [lo, hi] on the line p0 + t d with one earlier constraint (skipped when `use` is false).
+// Branch-light: the only divergent path is the division, taken when a bound actually moves (rare
+// once the first few constraints of a re-solve are in); comparisons by cross-multiplication.
+__device__ __forceinline__ void hpr_clip(const double4 c, bool use, double uL, double vL, double wL,
                                          double p0x, double p0y, double dx, double dy, double& lo,
                                          double& hi) {
   const double ax = c.x - uL, ay = c.y - vL, ah = c.z - wL;
   const double den = ax * dx + ay * dy;
   const double rhs = ah - (ax * p0x + ay * p0y);
-  if (den > 0.0) {
-    if (rhs > lo * den) lo = rhs / den;
-  } else if (den < 0.0) {
-    if (rhs > hi * den) hi = rhs / den;  // rhs/den < hi  <=>  rhs > hi*den  (den < 0)
-  } else if (rhs > 0.0) {
-    lo = INFINITY;
+  const bool pos = den > 0.0, neg = den < 0.0;
+  // den > 0: t >= rhs/den, moves lo when rhs > lo*den;  den < 0: t <= rhs/den, moves hi when
+  // rhs/den < hi  <=>  rhs > hi*den
+  const double bound = pos ? lo : hi;
+  const bool moves = use && (pos || neg) && rhs > bound * den;
+  if (moves) {
+    const double t = rhs / den;
+    if (pos) lo = t; else hi = t;
   }
+  if (use && !pos && !neg && rhs > 0.0) lo = INFINITY;
 }
 
 // Lane `L`'s optimum was cut off by constraint cj at position `pos` of the sequence q: the warp
 // solves the 1-D LP on cj's line over the constraints before `pos` (lane L's own point excluded by
-// index) and lane L takes the new optimum or becomes infeasible.
+// index) and lane L takes the new optimum or becomes infeasible.  UNROLL = loads in flight per lane
+// (q in shared memory: 4; q in global memory / L2: 8).
+template <int UNROLL>
 __device__ __forceinline__ void hpr_resolve(const double4* q, int pos, const double4 cj, int L,
                                             int lane, const double4 me, double& a, double& b,
                                             bool& feasible) {
@@ -268,54 +274,63 @@ __device__ __forceinline__ void hpr_resolve(const double4* q, int pos, const dou
     const double sc = h / nn;
     p0x = nx * sc, p0y = ny * sc;
     dx = -ny, dy = nx;
-    // box |p0 + t d| <= BOX
-    if (dx != 0.0) {
-      const double t1 = (-HPR_BOX - p0x) / dx, t2 = (HPR_BOX - p0x) / dx;
-      lo = fmax(lo, fmin(t1, t2));
-      hi = fmin(hi, fmax(t1, t2));
-    } else if (fabs(p0x) > HPR_BOX) {
-      ok = false;
-    }
-    if (dy != 0.0) {
-      const double t1 = (-HPR_BOX - p0y) / dy, t2 = (HPR_BOX - p0y) / dy;
-      lo = fmax(lo, fmin(t1, t2));
-      hi = fmin(hi, fmax(t1, t2));
-    } else if (fabs(p0y) > HPR_BOX) {
-      ok = false;
-    }
-    // all earlier constraints, split over the lanes, 4 loads in flight
+    // all earlier constraints, split over the lanes
     int k = lane;
-    for (; k + 96 < pos; k += 128) {
-      double4 c4[4];
+    for (; k + (UNROLL - 1) * 32 < pos; k += UNROLL * 32) {
+      double4 cu[UNROLL];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) c4[r] = q[k + 32 * r];
+      for (int r = 0; r < UNROLL; ++r) cu[r] = q[k + 32 * r];
 #pragma unroll
-      for (int r = 0; r < 4; ++r)
-        if (c4[r].w != iL) hpr_clip(c4[r], uL, vL, wL, p0x, p0y, dx, dy, lo, hi);
+      for (int r = 0; r < UNROLL; ++r)
+        hpr_clip(cu[r], cu[r].w != iL, uL, vL, wL, p0x, p0y, dx, dy, lo, hi);
     }
     for (; k < pos; k += 32) {
       const double4 c = q[k];
-      if (c.w != iL) hpr_clip(c, uL, vL, wL, p0x, p0y, dx, dy, lo, hi);
+      hpr_clip(c, c.w != iL, uL, vL, wL, p0x, p0y, dx, dy, lo, hi);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       lo = fmax(lo, __shfl_xor_sync(0xffffffffu, lo, o));
       hi = fmin(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    ok = ok && lo <= hi;
-  }
-  if (lane == L) {
-    if (!ok) {
-      feasible = false;
-    } else {
-      const double tt = (c0 * dx + c1 * dy > 0.0) ? hi : lo;
-      a = p0x + tt * dx;
-      b = p0y + tt * dy;
+    // the box |p0 + t d| <= BOX only matters on the side the objective pushes to while that side
+    // is still unbounded (the first few constraints of a sequence): its four divisions are skipped
+    // otherwise.  (A finite bound beyond the box is clamped by it all the same.)
+    const bool up = c0 * dx + c1 * dy > 0.0;
+    const double tsel = up ? hi : lo;
+    if (!(fabs(p0x + tsel * dx) <= HPR_BOX && fabs(p0y + tsel * dy) <= HPR_BOX)) {
+      if (dx != 0.0) {
+        const double t1 = (-HPR_BOX - p0x) / dx, t2 = (HPR_BOX - p0x) / dx;
+        lo = fmax(lo, fmin(t1, t2));
+        hi = fmin(hi, fmax(t1, t2));
+      } else if (fabs(p0x) > HPR_BOX) {
+        ok = false;
+      }
+      if (dy != 0.0) {
+        const double t1 = (-HPR_BOX - p0y) / dy, t2 = (HPR_BOX - p0y) / dy;
+        lo = fmax(lo, fmin(t1, t2));
+        hi = fmin(hi, fmax(t1, t2));
+      } else if (fabs(p0y) > HPR_BOX) {
+        ok = false;
+      }
     }
+    ok = ok && lo <= hi;
+    if (lane == L) {
+      if (!ok) {
+        feasible = false;
+      } else {
+        const double tt = up ? hi : lo;
+        a = p0x + tt * dx;
+        b = p0y + tt * dy;
+      }
+    }
+  } else if (lane == L) {
+    feasible = false;
   }
 }
 
 // the streaming part: constraints sq[0..cnt) are positions base.. of the sequence q
+template <int UNROLL>
 __device__ __forceinline__ void hpr_scan_tile(const double4* q, const double4* sq, int base, int cnt,
                                               int lane, const double4 me, double& a, double& b,
                                               bool& feasible) {
@@ -338,14 +353,14 @@ __device__ __forceinline__ void hpr_scan_tile(const double4* q, const double4* s
       while (m) {
         const int L = __ffs(m) - 1;
         m &= m - 1;
-        hpr_resolve(q, base + t, cj, L, lane, me, a, b, feasible);
+        hpr_resolve<UNROLL>(q, base + t, cj, L, lane, me, a, b, feasible);
       }
     }
   }
 }
 
 // FILTER: every point of the cloud against the extremes E (resident in shared memory).
-__global__ void __launch_bounds__(32 * HPR_FILTER_WARPS)
+__global__ void __launch_bounds__(32 * HPR_FILTER_WARPS, 3)  // <= 85 registers: 3 blocks (24 warps) per SM
 hpr_filter_kernel(int N, HprWs ws) {
   extern __shared__ double4 se[];
   const int v = blockIdx.y;
@@ -360,7 +375,7 @@ hpr_filter_kernel(int N, HprWs ws) {
   bool feasible = active;
   for (int base = 0; base < nE; base += HPR_TILE) {
     if (!__any_sync(0xffffffffu, feasible)) break;
-    hpr_scan_tile(se, se + base, base, min(HPR_TILE, nE - base), lane, me, a, b, feasible);
+    hpr_scan_tile<4>(se, se + base, base, min(HPR_TILE, nE - base), lane, me, a, b, feasible);
   }
   if (active) {
     ws.surv[(size_t)v * N + pi] = feasible ? 1 : 0;
@@ -368,18 +383,22 @@ hpr_filter_kernel(int N, HprWs ws) {
   }
 }
 
-// EXACT: the survivors against each other, continuing after the E prefix.  One warp per block:
-// warps re-solve at very different times, so nothing may couple them.
+// EXACT: the survivors against each other, continuing after the E prefix.  One warp per block
+// (warps re-solve at very different times, so nothing may couple them) and only HPR_EXACT_POINTS
+// points per warp: the warp-wide re-solves of its points are serialised, and they - not the
+// streaming scan - are what the pass spends its time on, so fewer points per warp (more warps in
+// flight) shortens every warp's critical path.
+static constexpr int HPR_EXACT_POINTS = 16;
 __global__ void __launch_bounds__(32)
 hpr_exact_kernel(int N, HprWs ws, uint8_t* __restrict__ vis) {
   __shared__ double4 sq[HPR_TILE];
   const int v = blockIdx.y;
   const int nC = ws.nC[v], nE = ws.nE[v];
   const int lane = threadIdx.x;
-  const int pi = blockIdx.x * 32 + lane;
-  if (blockIdx.x * 32 >= nC) return;
+  if (blockIdx.x * HPR_EXACT_POINTS >= nC) return;
+  const int pi = blockIdx.x * HPR_EXACT_POINTS + lane;
   const double4* q = ws.C + (size_t)v * N;
-  const bool active = pi < nC;
+  const bool active = lane < HPR_EXACT_POINTS && pi < nC;
   const double4 me = active ? q[pi] : make_double4(0.0, 0.0, 0.0, -1.0);
   const double2 ab0 = active ? ws.Cab[(size_t)v * N + pi] : make_double2(0.0, 0.0);
   double a = ab0.x, b = ab0.y;
@@ -391,7 +410,7 @@ hpr_exact_kernel(int N, HprWs ws, uint8_t* __restrict__ vis) {
     const int cnt = min(HPR_TILE, nC - base);
     for (int t = lane; t < cnt; t += 32) sq[t] = q[base + t];
     __syncwarp();
-    hpr_scan_tile(q, sq, base, cnt, lane, me, a, b, feasible);
+    hpr_scan_tile<8>(q, sq, base, cnt, lane, me, a, b, feasible);
   }
   if (active) vis[(size_t)v * N + (int)me.w] = feasible ? 1 : 0;
 }
@@ -440,7 +459,7 @@ int hpr_launch(const float* points, int N, int V, const double* frames_dev, doub
   PDR_COUNT_LAUNCH();
   hpr_compact_c_kernel<<<V, 1024, 0, stream>>>(N, stride, offset, ws, vis);
   PDR_COUNT_LAUNCH();
-  hpr_exact_kernel<<<dim3(cdiv(N, 32), V), 32, 0, stream>>>(N, ws, vis);
+  hpr_exact_kernel<<<dim3(cdiv(N, HPR_EXACT_POINTS), V), 32, 0, stream>>>(N, ws, vis);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;

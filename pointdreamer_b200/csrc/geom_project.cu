@@ -143,11 +143,14 @@ int project_launch(const float* cams, const float* vertices, int Vm, const float
 //                         (triangles spanning more than RT_MAX_SPAN tiles go to a per-view list);
 //   raster_scan_kernel    exclusive scan of the per-tile counts (one block);
 //   raster_bin_kernel     thread per (view, triangle): write the face id into the bins of its tiles;
-//   raster_tile_kernel    one CTA per tile, one THREAD PER PIXEL: the tile's triangle records are
-//                         staged through shared memory in chunks and every thread walks them,
-//                         keeping min (z, face id) in a register - no atomics, no z-buffer in global
-//                         memory - then writes depth / face id / masks (and the res/2 "any" mask of
-//                         demo.py:103-104) directly.
+//   raster_tile_kernel    one CTA per tile with the tile's z-buffer in SHARED memory: the tile's
+//                         triangle records are staged through shared memory in chunks, each warp
+//                         takes whole triangles and its lanes walk the triangle's bounding box
+//                         inside the tile (three exact fp64 edge functions per pixel), hits go to
+//                         the shared z-buffer with a shared-memory atomicMin on the packed
+//                         (z, face id) key - no global atomics, no z-buffer in global memory -
+//                         then thread = pixel writes depth / face id / masks (and the res/2 "any"
+//                         mask of demo.py:103-104) once, coalesced.
 // The result is the minimum over a SET of (z, id) keys, so the (non-deterministic) order of the
 // faces inside a bin does not matter: output is bit-identical to the one-warp-per-triangle +
 // atomicMin version it replaces, and to oracle/project.py:rasterize.
@@ -162,8 +165,24 @@ struct __align__(16) RasterTri {
 };
 static_assert(sizeof(RasterTri) == 64, "RasterTri must be 64 bytes");
 
+// Fast-path record of a triangle whose snapped coordinates are below 2^24: the three (sign-
+// normalised) edge functions e = A*px + B*py + C are evaluated in fp64, where every product and
+// sum is an integer below 2^53 and therefore EXACT - the same values as the int64 evaluation of
+// raster_shade, at 2 DFMA per edge instead of ~16 integer instructions.
+struct __align__(16) RasterEdge {
+  double A[3], B[3], C[3];  // edges opposite to vertex a, b, c
+  float thr[3];             // 0 when the edge owns its boundary pixels, 1 otherwise (e >= thr)
+  float az, bz, cz;
+  short x0, y0, x1, y1;     // pixel bounding box (clipped to the image)
+  int f;
+  int pad;
+};
+static_assert(sizeof(RasterEdge) == 112, "RasterEdge must be 112 bytes");
+static constexpr long long RT_EXACT_LIMIT = 1ll << 24;
+
 struct RasterWs {
   RasterTri* tris;     // [V*F]
+  RasterEdge* edges;   // [V*F]
   int* counts;         // [V*T + 1]  per-tile counts, then write cursors
   int* offs;           // [V*T + 1]  exclusive scan
   int* bins;           // [V*F*RT_MAX_SPAN]
@@ -178,6 +197,8 @@ static RasterWs raster_ws_carve(void* ws, int V, int F, int tiles) {
   RasterWs r;
   r.tris = (RasterTri*)w;
   w += rt_align((size_t)V * F * sizeof(RasterTri));
+  r.edges = (RasterEdge*)w;
+  w += rt_align((size_t)V * F * sizeof(RasterEdge));
   r.counts = (int*)w;
   w += rt_align(((size_t)V * tiles + 1) * 4);
   r.large_count = (int*)w;  // directly after counts: one memset clears both
@@ -192,7 +213,8 @@ static RasterWs raster_ws_carve(void* ws, int V, int F, int tiles) {
 
 size_t rasterize_workspace_bytes(int V, int F, int res) {
   const size_t tiles = (size_t)cdiv(res, RT_W) * cdiv(res, RT_H);
-  return rt_align((size_t)V * F * sizeof(RasterTri)) + 2 * rt_align(((size_t)V * tiles + 1) * 4) +
+  return rt_align((size_t)V * F * sizeof(RasterTri)) + rt_align((size_t)V * F * sizeof(RasterEdge)) +
+         2 * rt_align(((size_t)V * tiles + 1) * 4) +
          rt_align((size_t)V * 4) + rt_align((size_t)V * F * RT_MAX_SPAN * 4) +
          rt_align((size_t)V * F * 4) + 256;
 }
@@ -216,6 +238,13 @@ __device__ __forceinline__ bool raster_bbox(const RasterTri& t, int res, int& x0
   return true;
 }
 
+// every snapped coordinate below 2^24: the fp64 edge functions of RasterEdge are exact
+__device__ __forceinline__ bool raster_exact_range(const RasterTri& t) {
+  const long long m = max(max(max(llabs(t.ax), llabs(t.ay)), max(llabs(t.bx), llabs(t.by))),
+                          max(llabs(t.cx), llabs(t.cy)));
+  return m < RT_EXACT_LIMIT;
+}
+
 __global__ void raster_setup_kernel(const float* __restrict__ pos, const int* __restrict__ faces,
                                     int V, int Vm, int F, int res, int tiles_x, int tiles,
                                     RasterWs ws) {
@@ -235,9 +264,30 @@ __global__ void raster_setup_kernel(const float* __restrict__ pos, const int* __
   int x0, y0, x1, y1;
   if (!raster_bbox(t, res, x0, y0, x1, y1)) return;
   const int tx0 = x0 / RT_W, tx1 = x1 / RT_W, ty0 = y0 / RT_H, ty1 = y1 / RT_H;
-  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > RT_MAX_SPAN) {
+  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > RT_MAX_SPAN || !raster_exact_range(t)) {
     ws.large[(size_t)v * F + atomicAdd(&ws.large_count[v], 1)] = f;
     return;
+  }
+  {
+    const long long area = (t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax);
+    const long long sgn = area > 0 ? 1 : -1;
+    RasterEdge e;
+    // eA = sgn*((cx-bx)*(py-by) - (cy-by)*(px-bx)) = A*px + B*py + C with
+    const long long dxs[3] = {sgn * (t.cx - t.bx), sgn * (t.ax - t.cx), sgn * (t.bx - t.ax)};
+    const long long dys[3] = {sgn * (t.cy - t.by), sgn * (t.ay - t.cy), sgn * (t.by - t.ay)};
+    const long long ox[3] = {t.bx, t.cx, t.ax}, oy[3] = {t.by, t.cy, t.ay};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      e.A[k] = (double)(-dys[k]);
+      e.B[k] = (double)dxs[k];
+      e.C[k] = (double)(dys[k] * ox[k] - dxs[k] * oy[k]);
+      e.thr[k] = edge_inclusive(dxs[k], dys[k]) ? 0.0f : 1.0f;
+    }
+    e.az = t.az, e.bz = t.bz, e.cz = t.cz;
+    e.x0 = (short)x0, e.y0 = (short)y0, e.x1 = (short)x1, e.y1 = (short)y1;
+    e.f = f;
+    e.pad = 0;
+    ws.edges[i] = e;
   }
   for (int ty = ty0; ty <= ty1; ++ty)
     for (int tx = tx0; tx <= tx1; ++tx) atomicAdd(&ws.counts[(size_t)v * tiles + ty * tiles_x + tx], 1);
@@ -280,7 +330,7 @@ __global__ void raster_bin_kernel(int V, int F, int res, int tiles_x, int tiles,
   int x0, y0, x1, y1;
   if (!raster_bbox(t, res, x0, y0, x1, y1)) return;
   const int tx0 = x0 / RT_W, tx1 = x1 / RT_W, ty0 = y0 / RT_H, ty1 = y1 / RT_H;
-  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > RT_MAX_SPAN) return;
+  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > RT_MAX_SPAN || !raster_exact_range(t)) return;
   for (int ty = ty0; ty <= ty1; ++ty)
     for (int tx = tx0; tx <= tx1; ++tx) {
       const size_t tile = (size_t)v * tiles + ty * tiles_x + tx;
@@ -288,62 +338,93 @@ __global__ void raster_bin_kernel(int V, int F, int res, int tiles_x, int tiles,
     }
 }
 
-// coverage + depth of pixel centre (px, py) (sub-pixel units) for one triangle record
-__device__ __forceinline__ void raster_shade(const RasterTri& t, long long px, long long py,
-                                             unsigned long long& best) {
+// coverage + depth of pixel centre (px, py) (sub-pixel units) for one triangle record (int64 path);
+// returns the (z, face id) key or ~0
+__device__ __forceinline__ unsigned long long raster_shade(const RasterTri& t, long long px,
+                                                           long long py) {
   const long long area = (t.bx - t.ax) * (t.cy - t.ay) - (t.by - t.ay) * (t.cx - t.ax);
   const long long sgn = area > 0 ? 1 : -1;
   const long long eA = sgn * ((t.cx - t.bx) * (py - t.by) - (t.cy - t.by) * (px - t.bx));
   const long long eB = sgn * ((t.ax - t.cx) * (py - t.cy) - (t.ay - t.cy) * (px - t.cx));
   const long long eC = sgn * ((t.bx - t.ax) * (py - t.ay) - (t.by - t.ay) * (px - t.ax));
-  if (eA < 0 || eB < 0 || eC < 0) return;
+  if (eA < 0 || eB < 0 || eC < 0) return ~0ull;
   if ((eA == 0 && !edge_inclusive(sgn * (t.cx - t.bx), sgn * (t.cy - t.by))) ||
       (eB == 0 && !edge_inclusive(sgn * (t.ax - t.cx), sgn * (t.ay - t.cy))) ||
       (eC == 0 && !edge_inclusive(sgn * (t.bx - t.ax), sgn * (t.by - t.ay))))
-    return;
+    return ~0ull;
   const float wa = __ll2float_rn(eA), wb = __ll2float_rn(eB), wc = __ll2float_rn(eC);
   const float tot = __ll2float_rn(eA + eB + eC);
   const float z = ((wa * t.az + wb * t.bz) + wc * t.cz) / tot;
-  if (!(z >= -1.0f && z <= 1.0f)) return;
-  const unsigned long long key =
-      ((unsigned long long)float_to_ordered_u32(z) << 32) | (unsigned int)t.f;
-  best = min(best, key);
+  if (!(z >= -1.0f && z <= 1.0f)) return ~0ull;
+  return ((unsigned long long)float_to_ordered_u32(z) << 32) | (unsigned int)t.f;
 }
 
+// the same for a fast-path record: three exact fp64 edge functions
+__device__ __forceinline__ unsigned long long raster_shade_fast(const RasterEdge& t, double px,
+                                                                double py) {
+  const double eA = fma(t.A[0], px, fma(t.B[0], py, t.C[0]));
+  const double eB = fma(t.A[1], px, fma(t.B[1], py, t.C[1]));
+  const double eC = fma(t.A[2], px, fma(t.B[2], py, t.C[2]));
+  if (eA < (double)t.thr[0] || eB < (double)t.thr[1] || eC < (double)t.thr[2]) return ~0ull;
+  // integers below 2^53: double -> float rounds exactly like __ll2float_rn of the int64 value
+  const float wa = __double2float_rn(eA), wb = __double2float_rn(eB), wc = __double2float_rn(eC);
+  const float tot = __double2float_rn(eA + eB + eC);
+  const float z = ((wa * t.az + wb * t.bz) + wc * t.cz) / tot;
+  if (!(z >= -1.0f && z <= 1.0f)) return ~0ull;
+  return ((unsigned long long)float_to_ordered_u32(z) << 32) | (unsigned int)t.f;
+}
+
+// One CTA per 32 x 8 pixel tile, z-buffer of the tile in SHARED memory.  The tile's triangle records
+// are staged in shared memory RT_CHUNK at a time; each of the 8 warps takes whole triangles and its
+// lanes walk the part of the triangle's bounding box that lies inside the tile (16 x 2 pixels per
+// step), so the work is proportional to the covered area, not to triangles x tile pixels.  Hits go
+// to the shared z-buffer with a 64-bit shared-memory atomicMin on the packed (z, face id) key (the
+// minimum of a set: order independent); then thread = pixel writes all outputs once, coalesced.
 __global__ void __launch_bounds__(RT_W * RT_H)
 raster_tile_kernel(int V, int F, int res, int out_res, int tiles_x, int tiles, RasterWs ws,
                    float* __restrict__ depth, long long* __restrict__ face_idx,
                    uint8_t* __restrict__ mask_cam, uint8_t* __restrict__ mask_out) {
+  __shared__ RasterEdge se[RT_CHUNK];
   __shared__ RasterTri st[RT_CHUNK];
+  __shared__ unsigned long long zbuf[RT_H * RT_W];
   __shared__ int s_n;
   __shared__ uint8_t s_hit[RT_H][RT_W];
   const int tile = blockIdx.x % tiles, v = blockIdx.x / tiles;
   const int tx = tile % tiles_x, ty = tile / tiles_x;
-  const int lx = threadIdx.x % RT_W, ly = threadIdx.x / RT_W;
-  const int x = tx * RT_W + lx, y = ty * RT_H + ly;
-  const bool inside = x < res && y < res;
-  const long long px = (long long)x * SUBPIX + SUBPIX / 2, py = (long long)y * SUBPIX + SUBPIX / 2;
-  unsigned long long best = ~0ull;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sx = lane & 15, sy = lane >> 4;  // a warp step covers 16 x 2 pixels
+  const int X0 = tx * RT_W, X1 = min(X0 + RT_W, res) - 1, Y0 = ty * RT_H, Y1 = min(Y0 + RT_H, res) - 1;
   const RasterTri* tris = ws.tris + (size_t)v * F;
-  // ---- the tile's bin ----
+  const RasterEdge* edges = ws.edges + (size_t)v * F;
+  zbuf[threadIdx.x] = ~0ull;
+  // ---- the tile's bin (fast-path records) ----
   const int b0 = ws.offs[(size_t)v * tiles + tile], b1 = ws.offs[(size_t)v * tiles + tile + 1];
   for (int base = b0; base < b1; base += RT_CHUNK) {
     const int n = min(RT_CHUNK, b1 - base);
     __syncthreads();
-    // 4 threads copy one 64-byte record (16 bytes each)
-    for (int k = threadIdx.x; k < n * 4; k += RT_W * RT_H) {
-      const int r = k >> 2, part = k & 3;
-      reinterpret_cast<uint4*>(&st[r])[part] =
-          reinterpret_cast<const uint4*>(&tris[ws.bins[base + r]])[part];
+    // 7 threads copy one 112-byte record (16 bytes each)
+    for (int k = threadIdx.x; k < n * 7; k += RT_W * RT_H) {
+      const int r = k / 7, part = k - r * 7;
+      reinterpret_cast<uint4*>(&se[r])[part] =
+          reinterpret_cast<const uint4*>(&edges[ws.bins[base + r]])[part];
     }
     __syncthreads();
-    if (inside)
-      for (int r = 0; r < n; ++r) raster_shade(st[r], px, py, best);
+    for (int r = warp; r < n; r += RT_H) {
+      const RasterEdge& t = se[r];
+      const int x0 = max((int)t.x0, X0), x1 = min((int)t.x1, X1);
+      const int y0 = max((int)t.y0, Y0), y1 = min((int)t.y1, Y1);
+      for (int yy = y0 + sy; yy <= y1; yy += 2)
+        for (int xx = x0 + sx; xx <= x1; xx += 16) {
+          const unsigned long long key =
+              raster_shade_fast(t, (double)(xx * SUBPIX + SUBPIX / 2), (double)(yy * SUBPIX + SUBPIX / 2));
+          if (key != ~0ull) atomicMin(&zbuf[(yy - Y0) * RT_W + (xx - X0)], key);
+        }
+    }
   }
-  // ---- the view's large triangles (bounding box > RT_MAX_SPAN tiles), filtered per tile ----
+  // ---- the view's large triangles (bounding box > RT_MAX_SPAN tiles, or coordinates beyond the
+  //      exact fp64 range), filtered per tile, int64 edge functions ----
   const int nl = ws.large_count[v];
   const int* large = ws.large + (size_t)v * F;
-  const int X0 = tx * RT_W, X1 = min(X0 + RT_W, res) - 1, Y0 = ty * RT_H, Y1 = min(Y0 + RT_H, res) - 1;
   for (int base = 0; base < nl; base += RT_CHUNK) {
     __syncthreads();
     if (threadIdx.x == 0) s_n = 0;
@@ -356,9 +437,25 @@ raster_tile_kernel(int V, int F, int res, int out_res, int tiles_x, int tiles, R
     }
     __syncthreads();
     const int n = s_n;
-    if (inside)
-      for (int r = 0; r < n; ++r) raster_shade(st[r], px, py, best);
+    for (int r = warp; r < n; r += RT_H) {
+      const RasterTri& t = st[r];
+      int bx0, by0, bx1, by1;
+      raster_bbox(t, res, bx0, by0, bx1, by1);
+      const int x0 = max(bx0, X0), x1 = min(bx1, X1), y0 = max(by0, Y0), y1 = min(by1, Y1);
+      for (int yy = y0 + sy; yy <= y1; yy += 2)
+        for (int xx = x0 + sx; xx <= x1; xx += 16) {
+          const unsigned long long key = raster_shade(t, (long long)xx * SUBPIX + SUBPIX / 2,
+                                                      (long long)yy * SUBPIX + SUBPIX / 2);
+          if (key != ~0ull) atomicMin(&zbuf[(yy - Y0) * RT_W + (xx - X0)], key);
+        }
+    }
   }
+  __syncthreads();
+  // ---- thread = pixel: write the outputs ----
+  const int lx = threadIdx.x % RT_W, ly = threadIdx.x / RT_W;
+  const int x = X0 + lx, y = Y0 + ly;
+  const bool inside = x < res && y < res;
+  const unsigned long long best = zbuf[threadIdx.x];
   const bool hit = inside && best != ~0ull;
   if (inside) {
     const size_t p = ((size_t)v * res + y) * res + x;

@@ -516,25 +516,22 @@ struct GnApplyArgs {
 };
 
 // thread = fixed 8-channel chunk (affine constants live in registers), loops over pixels of its
-// block's slab with several 16-B loads in flight; grid = (pixel slabs, B)
-__device__ __forceinline__ void gn_transform_8(const uint4& v, const float (&ga)[8],
-                                               const float (&gb)[8], const float (&fs)[8],
-                                               const float (&fsh)[8], bool film, bool silu,
-                                               float (&y)[8]) {
-  const __half* h = (const __half*)&v;
+// block's slab with several 16-B loads in flight; grid = (pixel slabs, B).  The per-element math is
+// gn_apply_two (gn_math.cuh): packed half2 conversions, ~9 (plain) / ~12 (FiLM) instructions per
+// element instead of ~15 - the kernel is issue/MUFU-bound, not HBM-bound (2 MUFU per SiLU).
+struct GnConst {
+  float2 ga[4], gb[4], fsh[4];
+  __half2 fs[4];
+};
+template <bool FILM, bool SILU>
+__device__ __forceinline__ uint4 gn_transform_8(uint4 v, const GnConst& k) {
+  __half2* h = (__half2*)&v;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    y[j] = gn_apply_one(h2f(h[j]), ga[j], gb[j], fs[j], fsh[j], film, silu);  // gn_math.cuh
-  }
-}
-__device__ __forceinline__ uint4 pack_8(const float (&y)[8]) {
-  __align__(16) __half o[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = __float2half_rn(y[j]);
-  return *(const uint4*)o;
+  for (int j = 0; j < 4; ++j) h[j] = gn_apply_two<FILM, SILU>(h[j], k.ga[j], k.gb[j], k.fs[j], k.fsh[j]);
+  return v;
 }
 
-template <int RESAMPLE>
+template <int RESAMPLE, bool FILM, bool SILU>
 __global__ void __launch_bounds__(512, 2)  // <= 64 registers: 4 resident 256-thread CTAs per SM
 gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
   const int C = a.C1 + a.C2;
@@ -544,8 +541,6 @@ gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
   const int b = blockIdx.y;
   const int c0 = chunk * 8;
   const int cpg = C / 32;
-  const bool film = a.film != nullptr, silu = a.silu != 0;
-  float ga[8], gb[8], fs[8], fsh[8];
   float mean8 = 0.f, rstd8 = 0.f;
   if (a.sums1) {
     // statistics straight from the conv epilogue's sums (cpg is a multiple of 8 here, so the
@@ -565,27 +560,33 @@ gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
     mean8 = (float)mean;
     rstd8 = (float)(1.0 / sqrt(var + 1e-5));
   }
+  GnConst k;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = c0 + j;
     const int g = c / cpg;
     const float mean = a.sums1 ? mean8 : a.stats[((size_t)b * 32 + g) * 2];
     const float rstd = a.sums1 ? rstd8 : a.stats[((size_t)b * 32 + g) * 2 + 1];
-    ga[j] = rstd * a.gamma[c];
-    gb[j] = a.beta[c] - mean * ga[j];
-    if (film) {
+    const float ga = rstd * a.gamma[c];
+    const float gb = a.beta[c] - mean * ga;
+    float fs = 1.f, fsh = 0.f;
+    if (FILM) {
       const __half* f = a.film + (size_t)b * a.film_stride + a.film_off;
-      fs[j] = round_h(1.0f + h2f(f[c]));  // (1 + scale) in fp16
-      fsh[j] = h2f(f[C + c]);
+      fs = round_h(1.0f + h2f(f[c]));  // (1 + scale) in fp16
+      fsh = h2f(f[C + c]);
+    }
+    if (j & 1) {
+      k.ga[j / 2].y = ga, k.gb[j / 2].y = gb, k.fsh[j / 2].y = fsh;
+      k.fs[j / 2] = __halves2half2(__low2half(k.fs[j / 2]), __float2half_rn(fs));
     } else {
-      fs[j] = 1.f, fsh[j] = 0.f;
+      k.ga[j / 2].x = ga, k.gb[j / 2].x = gb, k.fsh[j / 2].x = fsh;
+      k.fs[j / 2] = __halves2half2(__float2half_rn(fs), __float2half_rn(fs));
     }
   }
   const __half* src = c0 < a.C1 ? a.x1 + c0 : a.x2 + (c0 - a.C1);
   const size_t sstride = c0 < a.C1 ? a.C1 : a.C2;
   const int H = a.H, W = a.W;
   src += (size_t)b * H * W * sstride;
-  float y[8];
   if (RESAMPLE == 0) {
     __half* dst = a.out + (size_t)b * H * W * C + c0;
     const int npix = H * W;
@@ -596,15 +597,12 @@ gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[u] = __ldg((const uint4*)(src + (size_t)(p + u * planes) * sstride));
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        gn_transform_8(v[u], ga, gb, fs, fsh, film, silu, y);
-        *(uint4*)(dst + (size_t)(p + u * planes) * C) = pack_8(y);
-      }
+      for (int u = 0; u < 4; ++u)
+        *(uint4*)(dst + (size_t)(p + u * planes) * C) = gn_transform_8<FILM, SILU>(v[u], k);
     }
     for (; p < p1; p += planes) {
       const uint4 v = __ldg((const uint4*)(src + (size_t)p * sstride));
-      gn_transform_8(v, ga, gb, fs, fsh, film, silu, y);
-      *(uint4*)(dst + (size_t)p * C) = pack_8(y);
+      *(uint4*)(dst + (size_t)p * C) = gn_transform_8<FILM, SILU>(v, k);
     }
   } else if (RESAMPLE == 1) {  // AvgPool2d(2) of the activated tensor: loop over OUTPUT pixels
     const int Ho = H / 2, Wo = W / 2;
@@ -617,18 +615,24 @@ gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         v[u] = __ldg((const uint4*)(src + ((size_t)(2 * yo + (u >> 1)) * W + 2 * xo + (u & 1)) * sstride));
-      float acc[8];
+      float2 acc[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        gn_transform_8(v[u], ga, gb, fs, fsh, film, silu, y);
+        const uint4 t = gn_transform_8<FILM, SILU>(v[u], k);
+        const __half2* th = (const __half2*)&t;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += y[j];
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(th[j]);
+          acc[j].x += f.x, acc[j].y += f.y;
+        }
       }
+      uint4 o;
+      __half2* oh = (__half2*)&o;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = acc[j] * 0.25f;
-      *(uint4*)(dst + (size_t)p * C) = pack_8(y);
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[j].x * 0.25f, acc[j].y * 0.25f);
+      *(uint4*)(dst + (size_t)p * C) = o;
     }
   } else {  // nearest x2: loop over INPUT pixels, write the 2x2 block
     const int Wo = W * 2;
@@ -638,8 +642,7 @@ gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
     for (int p = p0 + plane; p < p1; p += planes) {
       const int yi = p / W, xi = p - yi * W;
       const uint4 v = __ldg((const uint4*)(src + (size_t)p * sstride));
-      gn_transform_8(v, ga, gb, fs, fsh, film, silu, y);
-      const uint4 o = pack_8(y);
+      const uint4 o = gn_transform_8<FILM, SILU>(v, k);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         *(uint4*)(dst + ((size_t)(2 * yi + (u >> 1)) * Wo + 2 * xi + (u & 1)) * C) = o;
@@ -732,12 +735,21 @@ int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int
   int ppb = planes * 32;  // ~32 pixels per thread
   while (ppb > planes && (long long)cdiv(npix, ppb) * B < 148 * 4) ppb /= 2;
   dim3 grid(cdiv(npix, ppb), B);
+  const bool fl = film != nullptr, si = silu != 0;
+#define PDR_GN_CASE(R)                                                                      \
+  do {                                                                                      \
+    if (fl && si) gn_apply_kernel<R, true, true><<<grid, threads, 0, stream>>>(a, ppb);     \
+    else if (fl) gn_apply_kernel<R, true, false><<<grid, threads, 0, stream>>>(a, ppb);     \
+    else if (si) gn_apply_kernel<R, false, true><<<grid, threads, 0, stream>>>(a, ppb);     \
+    else gn_apply_kernel<R, false, false><<<grid, threads, 0, stream>>>(a, ppb);            \
+  } while (0)
   if (resample == 0)
-    gn_apply_kernel<0><<<grid, threads, 0, stream>>>(a, ppb);
+    PDR_GN_CASE(0);
   else if (resample == 1)
-    gn_apply_kernel<1><<<grid, threads, 0, stream>>>(a, ppb);
+    PDR_GN_CASE(1);
   else
-    gn_apply_kernel<2><<<grid, threads, 0, stream>>>(a, ppb);
+    PDR_GN_CASE(2);
+#undef PDR_GN_CASE
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;
