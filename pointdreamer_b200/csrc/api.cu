@@ -29,9 +29,11 @@ int pdr_conv_tc(const void* x1, const void* x2, const void* w, const float* bias
     PDR_TRY(conv_tc_make_act_map(&ma2, x2, B, H, W, C2, halo));
   }
   PDR_TRY(conv_tc_make_weight_map(&mw, w, Cout, taps * (C1 + C2), bn == 512 ? 128 : bn));
+  ConvTensorMap mo;
+  if (!halo) PDR_TRY(conv_tc_make_act_map(&mo, out, B, H, W, Cout, 0));
   return conv_tc_launch(&ma1, C2 > 0 ? &ma2 : nullptr, &mw, bn, B, H, W, C1, C2, Cout, taps, bias,
                         (const __half*)residual, (__half*)out, nullptr, (cudaStream_t)stream, 0.f,
-                        nullptr, nullptr, 0, 0, 1, nullptr, halo);
+                        nullptr, nullptr, 0, 0, 1, nullptr, halo, nullptr, 0, halo ? nullptr : &mo);
 }
 
 int pdr_conv_tc_skip(const void* x, const void* w, const float* bias, const void* s1,

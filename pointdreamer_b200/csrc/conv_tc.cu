@@ -60,23 +60,38 @@ struct ConvArgs {
   // (image, input channel of cat(A1, A2)); null = the input is already activated
   const float4* gn_coeff;
   int gn_film;
+  // plain kernels: the epilogue stages each 128-pixel x 64-channel block of the output tile in
+  // shared memory (128-byte swizzle) and writes it with ONE TMA store (cp.async.bulk.tensor,
+  // UTMASTG) instead of 16-byte row-strided stores from every thread
+  int tma_store;
 };
+
+static constexpr int OUT_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB, one TMA-store box
 
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int OUT_STAGE_OFFSET = STAGES * STAGE_BYTES;  // 2 x [128 px][64 ch] fp16
+  static constexpr int BAR_OFFSET = OUT_STAGE_OFFSET + 2 * OUT_STAGE_BYTES;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem ptr
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
 };
 
 // One output tile of the epilogue for the calling warp (TMEM lane quadrant q): TMEM -> registers ->
 // +bias (+residual) -> fp16 -> global, plus the optional deterministic GroupNorm partial sums.
+// TMA-store state of the epilogue warps of one CTA: staging buffers + how many 64-channel blocks
+// have been issued so far (same value in all 128 epilogue threads)
+struct OutStage {
+  uint8_t* buf = nullptr;        // 2 x OUT_STAGE_BYTES, 1024-byte aligned; null = direct stores
+  const CUtensorMap* map = nullptr;
+  uint32_t blocks = 0;
+};
+
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint32_t tmem_acc, int m_lin,
-                                              int n_tile, int q, int lane) {
+                                              int n_tile, int q, int lane, OutStage* os = nullptr) {
   const int r = q * 32 + lane;  // row of the tile == TMEM lane
   const int pw = r % args.bw;
   const int ph = (r / args.bw) % args.bh;
@@ -144,9 +159,18 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint32_t tme
                 __float2half_rn(__half2float(o[j * 8 + e]) + __half2float(rh[e]));
         }
       }
-      uint4* op = (uint4*)(args.out + row_off + ch * 32);
+      if (os == nullptr) {
+        uint4* op = (uint4*)(args.out + row_off + ch * 32);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) op[j] = ((const uint4*)o)[j];
+        for (int j = 0; j < 4; ++j) op[j] = ((const uint4*)o)[j];
+      } else {
+        // this thread's 64 bytes of row r of the staged block: 16-byte chunk c of a row lives at
+        // (c ^ (r & 7)) - the layout a SWIZZLE_128B tensor map expects
+        uint8_t* dst = os->buf + (os->blocks & 1) * OUT_STAGE_BYTES + r * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *(uint4*)(dst + ((((ch & 1) * 4 + j) ^ (r & 7)) << 4)) = ((const uint4*)o)[j];
+      }
       if (args.stats_partial) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -205,6 +229,20 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& args, uint32_t tme
                     args.stats_partial[(((size_t)m_lin * 4 + q) * (args.Cout / 8) + (n0 + ch * 32) / 8 + g) * 2 +
                            is_q] = x1;
       }
+    }
+    if (os != nullptr && (ch & 1)) {
+      // both 32-channel halves of the block are staged: make the generic-proxy writes visible to
+      // the async proxy, gather the four epilogue warps, one thread issues the store
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (q == 0 && lane == 0) {
+        tma_store_4d(os->map, os->buf + (os->blocks & 1) * OUT_STAGE_BYTES, n0 + (ch >> 1) * 64,
+                     tx * args.bw, ty * args.bh, tb * args.bb);
+        bulk_commit_group();
+        bulk_wait_group_read<1>();  // the OTHER buffer (issued one block ago) has been read
+      }
+      ++os->blocks;
+      named_bar_sync(1, 128);  // ... so everybody may overwrite it
     }
   }
 }
@@ -273,7 +311,8 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmS1,
-               const __grid_constant__ CUtensorMap tmS2, const ConvArgs args) {
+               const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmO,
+               const ConvArgs args) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-B aligned by the ABI: realign to 1024 B for SWIZZLE_128B
@@ -302,6 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     tma_prefetch_desc(&tmA1);
     if (args.C2 > 0) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
+    if (args.tma_store) tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -418,6 +458,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
+    OutStage os;
+    const bool tma_out = args.tma_store && ksplit == 1;
+    if (tma_out) {
+      os.buf = smem + L::OUT_STAGE_OFFSET;
+      os.map = &tmO;
+    }
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
       const int tile = work / ksplit;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -427,7 +473,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
                              tile % args.tiles_n, work - tile * ksplit, q, lane);
       else
         epilogue_tile<BN>(args, tmem_base + (uint32_t)(acc * BN), tile / args.tiles_n,
-                          tile % args.tiles_n, q, lane);
+                          tile % args.tiles_n, q, lane, tma_out ? &os : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -436,6 +482,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         acc_phase ^= 1;
       }
     }
+    if (tma_out && q == 0 && lane == 0) bulk_wait_group<0>();  // stores complete before exit
   }
 
   tc_fence_before();
@@ -458,7 +505,8 @@ struct SmemLayout2 {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = 128 * BLOCK_K * 2;  // this CTA's half of the 256-row B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int OUT_STAGE_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = OUT_STAGE_OFFSET + 2 * OUT_STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16;
 };
 
@@ -466,7 +514,8 @@ template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmS1,
-                const __grid_constant__ CUtensorMap tmS2, const ConvArgs args) {
+                const __grid_constant__ CUtensorMap tmS2, const __grid_constant__ CUtensorMap tmO,
+                const ConvArgs args) {
   constexpr int BN = 256;
   using L = SmemLayout2<STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -611,11 +660,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    OutStage os;
+    if (args.tma_store) {
+      os.buf = smem + L::OUT_STAGE_OFFSET;
+      os.map = &tmO;
+    }
     for (int pair = cluster_id; pair < num_pairs; pair += num_clusters) {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<BN>(args, tmem_base + (uint32_t)(acc * BN),
-                        (pair / args.tiles_n) * 2 + (int)rank, pair % args.tiles_n, q, lane);
+                        (pair / args.tiles_n) * 2 + (int)rank, pair % args.tiles_n, q, lane,
+                        args.tma_store ? &os : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // the leader's barrier
@@ -624,6 +679,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         acc_phase ^= 1;
       }
     }
+    if (args.tma_store && q == 0 && lane == 0) bulk_wait_group<0>();  // stores complete before exit
   }
 
   tc_fence_before();
@@ -1147,8 +1203,8 @@ size_t conv_tc_split_workspace_bytes(int B, int H, int W, int Cout, int ksplit) 
 
 template <int BN, int STAGES>
 static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
-                       const ConvTensorMap* s1, const ConvTensorMap* s2, const ConvArgs& args,
-                       cudaStream_t stream) {
+                       const ConvTensorMap* s1, const ConvTensorMap* s2, const ConvTensorMap* o,
+                       const ConvArgs& args, cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES>;
   constexpr int smem_bytes = L::TOTAL + 1024;  // +1024 for the manual realignment
   static bool configured = false;
@@ -1161,7 +1217,8 @@ static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const C
   int grid = tiles < num_sms() ? tiles : num_sms();
   conv_tc_kernel<BN, STAGES><<<grid, NUM_THREADS, smem_bytes, stream>>>(
       *(const CUtensorMap*)a1, *(const CUtensorMap*)(a2 ? a2 : a1), *(const CUtensorMap*)w,
-      *(const CUtensorMap*)(s1 ? s1 : a1), *(const CUtensorMap*)(s2 ? s2 : (s1 ? s1 : a1)), args);
+      *(const CUtensorMap*)(s1 ? s1 : a1), *(const CUtensorMap*)(s2 ? s2 : (s1 ? s1 : a1)),
+      *(const CUtensorMap*)(o ? o : a1), args);
   PDR_COUNT_LAUNCH();
   if (args.ksplit > 1) {
     const long long n = (long long)args.tiles_b * args.tiles_y * args.tiles_x * BLOCK_M *
@@ -1175,8 +1232,8 @@ static int launch_impl(const ConvTensorMap* a1, const ConvTensorMap* a2, const C
 
 template <int STAGES>
 static int launch_impl2(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvTensorMap* w,
-                        const ConvTensorMap* s1, const ConvTensorMap* s2, const ConvArgs& args,
-                        cudaStream_t stream) {
+                        const ConvTensorMap* s1, const ConvTensorMap* s2, const ConvTensorMap* o,
+                        const ConvArgs& args, cudaStream_t stream) {
   using L = SmemLayout2<STAGES>;
   constexpr int smem_bytes = L::TOTAL + 1024;
   static bool configured = false;
@@ -1189,7 +1246,8 @@ static int launch_impl2(const ConvTensorMap* a1, const ConvTensorMap* a2, const 
   int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
   conv_tc2_kernel<STAGES><<<2 * clusters, NUM_THREADS, smem_bytes, stream>>>(
       *(const CUtensorMap*)a1, *(const CUtensorMap*)(a2 ? a2 : a1), *(const CUtensorMap*)w,
-      *(const CUtensorMap*)(s1 ? s1 : a1), *(const CUtensorMap*)(s2 ? s2 : (s1 ? s1 : a1)), args);
+      *(const CUtensorMap*)(s1 ? s1 : a1), *(const CUtensorMap*)(s2 ? s2 : (s1 ? s1 : a1)),
+      *(const CUtensorMap*)(o ? o : a1), args);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;
@@ -1241,8 +1299,9 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
                    const float* bias, const __half* residual, __half* out, float* stats_partial,
                    cudaStream_t stream, float qk_scale, const ConvTensorMap* s1,
                    const ConvTensorMap* s2, int S1, int S2, int ksplit, float* splitk_ws,
-                   int halo, const float4* gn_coeff, int gn_film) {
+                   int halo, const float4* gn_coeff, int gn_film, const ConvTensorMap* omap) {
   PDR_CHECK_ARG(gn_coeff == nullptr || halo, "a fused GroupNorm needs the halo kernel");
+  static const bool no_tma_store = getenv("PDR_NO_TMA_STORE") != nullptr;  // A/B switch
   PDR_CHECK_ARG(!halo || (conv_tc_halo_ok(H, W, taps) && ksplit == 1),
                 "halo mode needs a 3x3 conv on a map with W %% 8 == 0, H %% 16 == 0 and no split-K");
   PDR_CHECK_ARG(ksplit >= 1 && (ksplit == 1 || (splitk_ws != nullptr && BN != 512 &&
@@ -1288,6 +1347,7 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
   args.qk_scale = qk_scale;
   args.ksplit = ksplit;
   args.splitk_ws = splitk_ws;
+  args.tma_store = (omap != nullptr && !halo && ksplit == 1 && !no_tma_store) ? 1 : 0;
   PDR_CHECK_ARG(qk_scale == 0.f || (Cout % 192 == 0 && !residual && !stats_partial),
                 "qk_scale is for qkv projections (Cout %% 192 == 0, no residual, no statistics)");
   PDR_CHECK_ARG(!stats_partial || (args.bb == 1 && Cout % 32 == 0),
@@ -1296,16 +1356,16 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
     PDR_CHECK_ARG((args.tiles_b * args.tiles_y * args.tiles_x) % 2 == 0,
                   "2-CTA conv needs an even number of 128-pixel tiles");
     if (halo) return launch_halo<true, 256, 3, 9>(a1, a2, w, s1, s2, args, stream);
-    return launch_impl2<6>(a1, a2, w, s1, s2, args, stream);
+    return launch_impl2<6>(a1, a2, w, s1, s2, omap, args, stream);
   }
   if (halo) {
     if (BN == 256) return launch_halo<false, 256, 2, 5>(a1, a2, w, s1, s2, args, stream);
     if (BN == 128) return launch_halo<false, 128, 3, 9>(a1, a2, w, s1, s2, args, stream);
     return launch_halo<false, 64, 3, 12>(a1, a2, w, s1, s2, args, stream);
   }
-  if (BN == 256) return launch_impl<256, 4>(a1, a2, w, s1, s2, args, stream);
-  if (BN == 128) return launch_impl<128, 6>(a1, a2, w, s1, s2, args, stream);
-  return launch_impl<64, 8>(a1, a2, w, s1, s2, args, stream);
+  if (BN == 256) return launch_impl<256, 4>(a1, a2, w, s1, s2, omap, args, stream);
+  if (BN == 128) return launch_impl<128, 6>(a1, a2, w, s1, s2, omap, args, stream);
+  return launch_impl<64, 8>(a1, a2, w, s1, s2, omap, args, stream);
 }
 
 }  // namespace pdr

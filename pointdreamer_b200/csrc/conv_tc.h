@@ -41,7 +41,10 @@ int conv_tc_launch(const ConvTensorMap* a1, const ConvTensorMap* a2, const ConvT
                    cudaStream_t stream, float qk_scale = 0.f, const ConvTensorMap* s1 = nullptr,
                    const ConvTensorMap* s2 = nullptr, int S1 = 0, int S2 = 0, int ksplit = 1,
                    float* splitk_ws = nullptr, int halo = 0, const float4* gn_coeff = nullptr,
-                   int gn_film = 0);
+                   int gn_film = 0, const ConvTensorMap* omap = nullptr);
+// omap (plain kernels only): tensor map of `out` made by conv_tc_make_act_map(out, B, H, W, Cout);
+// the epilogue then stages 128-pixel x 64-channel blocks in shared memory and writes them with TMA
+// stores instead of per-thread 16-byte stores
 // gn_coeff (halo kernel only): the A maps point at the RAW tensor and GroupNorm32 (+FiLM when
 // gn_film) + SiLU is applied to each halo tile in shared memory with the constants of
 // gn_coeff_launch (unet_ops.h): float4 (ga, gb, fs, fsh) per (image, channel of cat(A1, A2))

@@ -86,7 +86,7 @@ class Planner {
 };
 
 struct ConvOp {
-  ConvTensorMap a1, a2, w, s1, s2;
+  ConvTensorMap a1, a2, w, s1, s2, o;
 };
 
 class UnetEngine {
@@ -341,6 +341,8 @@ class UnetEngine {
     if (skip2)
       PDR_TRY(conv_tc_make_act_map(&c->s2, P<__half>(skip2->off), B_, skip2->H, skip2->W, Cs2,
                                    halo));
+    const bool tma_out = !halo && ksplit == 1;  // plain kernels write their tiles with TMA stores
+    if (tma_out) PDR_TRY(conv_tc_make_act_map(&c->o, P<__half>(out.off), B_, out.H, out.W, out.C, 0));
     const bool hs1 = skip1 != nullptr, hs2 = skip2 != nullptr;
     const int H = out.H, W = out.W, C1 = x1.C, C2 = x2 ? x2->C : 0, Co = out.C, Bn = B_;
     const float* bias = (const float*)b->ptr;
@@ -355,7 +357,7 @@ class UnetEngine {
       return conv_tc_launch(&c->a1, has2 ? &c->a2 : nullptr, &c->w, bn, Bn, H, W, C1, C2, Co, taps,
                             bias, r, o, partial, s, qk_scale, hs1 ? &c->s1 : nullptr,
                             hs2 ? &c->s2 : nullptr, Cs1, Cs2, ksplit, split_ws, halo, coeff,
-                            gn_film);
+                            gn_film, tma_out ? &c->o : nullptr);
     });
     if (stat_rows > 0) {
       double* sums = P<double>(out.sums_off);
