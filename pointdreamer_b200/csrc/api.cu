@@ -111,7 +111,7 @@ int pdr_unet_plan(void* handle, int B, void* workspace, size_t bytes) {
 }
 int pdr_unet_forward(void* handle, const float* x, const float* t, float* out, int n_out,
                      void* stream) {
-  return unet_forward(handle, x, t, out, n_out, (cudaStream_t)stream);
+  return unet_forward_serialized(handle, x, t, out, n_out, (cudaStream_t)stream);
 }
 
 int pdr_unet_profile_begin(void* handle, int every, int max_forwards) {

@@ -875,6 +875,45 @@ static int unet_forward_graphed(UnetEngine* e, const float* x, float* out, int n
   return 0;
 }
 
+// Engines of one process are serialised on the device: work submitted through the public entry
+// points (pdr_unet_forward, pdr_ddnm_sample) waits for the previous submission of ANY engine on ANY
+// stream of the same device.  The tcgen05 conv kernels are persistent, allocate all of an SM's
+// tensor memory and (2-CTA variants) need both SMs of a pair; in round 1 four engines driven from
+// four streams hung a box once.  Running them concurrently cannot be faster anyway - one engine
+// already holds the GPU at its 1 kW power limit (profiles/r02f_power_probe.json) - so the library
+// orders them instead of leaving the interleaving to the hardware scheduler.
+struct DeviceTurn {
+  cudaEvent_t ev = nullptr;
+  bool recorded = false;
+};
+static DeviceTurn g_turn[64];
+static DeviceTurn* device_turn() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  DeviceTurn* t = &g_turn[dev];
+  if (!t->ev && cudaEventCreateWithFlags(&t->ev, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return t;
+}
+static void turn_begin(cudaStream_t stream) {
+  DeviceTurn* t = device_turn();
+  if (t && t->recorded) cudaStreamWaitEvent(stream, t->ev, 0);
+}
+static void turn_end(cudaStream_t stream) {
+  DeviceTurn* t = device_turn();
+  if (t && cudaEventRecord(t->ev, stream) == cudaSuccess) t->recorded = true;
+}
+
+int unet_forward_serialized(void* handle, const float* x, const float* t, float* out, int n_out,
+                            cudaStream_t stream) {
+  turn_begin(stream);
+  const int rc = unet_forward(handle, x, t, out, n_out, stream);
+  turn_end(stream);
+  return rc;
+}
+
 // DDNM chain for V views at once (diffusion.py:459-570): prepare, `steps` x (U-Net + fused update),
 // final transform.  coef_host: [steps][7] floats (DdnmStepCoef order); t_dev: [steps][V] device.
 int ddnm_sample(void* handle, const float* sparse, const float* mask, int V, int steps,
@@ -889,6 +928,11 @@ int ddnm_sample(void* handle, const float* sparse, const float* mask, int V, int
   PDR_CHECK_ARG(draws_per_chain >= (unsigned long long)steps + 1,
                 "ddnm_sample: draws_per_chain must be >= steps + 1");
   const int S = e->cfg.image_size;
+  turn_begin(stream);
+  struct TurnEnd {
+    cudaStream_t s;
+    ~TurnEnd() { turn_end(s); }
+  } turn_guard{stream};
   PDR_TRY(ddnm_prepare_launch(sparse, mask, V, 3, S, S, seed, offset_base, draws_per_chain, chain0,
                               y, x, stream));
   for (int s = 0; s < steps; ++s) {

@@ -14,6 +14,9 @@ int unet_plan(void* handle, int B, void* workspace, size_t bytes);
 // out: [B, n_out, S, S] fp32 (first n_out of the model's output channels)
 int unet_forward(void* handle, const float* x, const float* t, float* out, int n_out,
                  cudaStream_t stream);
+// the public entry: the same, ordered after the previous submission of any engine on this device
+int unet_forward_serialized(void* handle, const float* x, const float* t, float* out, int n_out,
+                            cudaStream_t stream);
 int ddnm_sample(void* handle, const float* sparse, const float* mask, int V, int steps,
                 const float* coef_host, const float* t_dev, unsigned long long seed,
                 unsigned long long offset_base, unsigned long long draws_per_chain, int chain0,

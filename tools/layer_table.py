@@ -59,7 +59,9 @@ def layers():
 
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if not l.startswith("==")) if len(r) > 10 and r[0].isdigit()]
 heads = [i for i, r in enumerate(rows) if "head_kernel" in r[4]]
-fw = rows[heads[0] + 1:heads[1] + 1]
+# a bench.py launch list holds several forwards delimited by head_kernel launches; a conv-only
+# list (ncu -k regex:conv..., one forward of tools/bench_unet.py) is taken whole
+fw = rows[heads[0] + 1:heads[1] + 1] if len(heads) >= 2 else rows
 launches = []
 for r in fw:
     name = r[4].split("(")[0].replace("void ", "")
