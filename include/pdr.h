@@ -79,6 +79,9 @@ int pdr_group_norm(const void* x1, const void* x2, int B, int H, int W, int C1, 
                    void* stream);
 int pdr_resample(const void* x, int B, int H, int W, int C, int mode, void* out, void* stream);
 int pdr_attention(const void* qkv, int B, int T, int heads, void* out, void* stream);
+/* the same with q and k ALREADY multiplied by 64^-1/4 and rounded to fp16 (what the engine's qkv
+ * projection emits); sequences with T % 128 == 0 run on tcgen05 (S and O in tensor memory) */
+int pdr_attention_prescaled(const void* qkv, int B, int T, int heads, void* out, void* stream);
 int pdr_unet_head(const void* h, const float* gamma, const float* beta, const float* w,
                   const float* bias, int B, int H, int W, int C, int n_out, float* ws,
                   float* stats, float* out, void* stream);

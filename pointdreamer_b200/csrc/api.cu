@@ -88,6 +88,10 @@ int pdr_attention(const void* qkv, int B, int T, int heads, void* out, void* str
   PDR_CHECK_ARG(qkv && out, "pdr_attention: null pointer");
   return attention_launch((const __half*)qkv, B, T, heads, 0, (__half*)out, (cudaStream_t)stream);
 }
+int pdr_attention_prescaled(const void* qkv, int B, int T, int heads, void* out, void* stream) {
+  PDR_CHECK_ARG(qkv && out, "pdr_attention_prescaled: null pointer");
+  return attention_launch((const __half*)qkv, B, T, heads, 1, (__half*)out, (cudaStream_t)stream);
+}
 int pdr_unet_head(const void* h, const float* gamma, const float* beta, const float* w,
                   const float* bias, int B, int H, int W, int C, int n_out, float* ws,
                   float* stats, float* out, void* stream) {

@@ -238,6 +238,8 @@ int attention_launch(const __half* qkv, int B, int T, int heads, int prescaled, 
                      cudaStream_t stream) {
   PDR_CHECK_ARG(T % 64 == 0 && T >= 64, "attention: sequence length %d must be a multiple of 64", T);
   PDR_CHECK_ARG(heads >= 1 && B >= 1, "attention: bad shape");
+  // sequences of >= 128 tokens with pre-scaled q, k (the engine's case): tensor-memory version
+  if (attention_tc_ok(T, prescaled)) return attention_tc_launch(qkv, B, T, heads, out, stream);
   // 128 queries per CTA halves the K/V re-reads; small maps keep 64 so the grid still fills
   if (T % 128 == 0 && (T / 128) * heads * B >= 2 * 148)
     return attention_launch_nw<8>(qkv, B, T, heads, prescaled, out, stream);

@@ -1115,6 +1115,24 @@ int conv_tc_make_weight_map(ConvTensorMap* out, const void* ptr, int Cout, int K
   return 0;
 }
 
+int conv_tc_make_map_2d(ConvTensorMap* out, const void* ptr, unsigned long long inner,
+                        unsigned long long outer, int box_inner, int box_outer) {
+  EncodeTiledFn enc = get_encode_fn();
+  PDR_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable");
+  PDR_CHECK_ARG(box_inner * 2 == 128 && box_outer >= 1 && box_outer <= 256 && inner % 8 == 0,
+                "2-D map: the box must be 128 bytes wide and at most 256 rows");
+  PDR_CHECK_ARG(((uintptr_t)ptr & 15) == 0, "2-D map: pointer must be 16-byte aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)inner * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)ptr, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PDR_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d) failed: CUresult %d", (int)r);
+  return 0;
+}
+
 int conv_tc_stats_rows_per_image(int H, int W) {
   int bw, bh, bb;
   conv_tc_pick_box(1, H, W, &bw, &bh, &bb);

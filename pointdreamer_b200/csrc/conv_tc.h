@@ -24,6 +24,10 @@ int conv_tc_make_act_map(ConvTensorMap* out, const void* ptr, int B, int H, int 
 // 3x3 convs on maps with W % 8 == 0 and H % 16 == 0 run the halo kernel: all nine taps of a
 // 64-channel chunk read ONE shared-memory tile (activation maps must be encoded with halo = 1)
 bool conv_tc_halo_ok(int H, int W, int taps);
+// generic 2-D fp16 map (SWIZZLE_128B): matrix [outer][inner] with `inner` contiguous, box
+// {box_inner (64 = 128 bytes), box_outer}; used by the tcgen05 attention for the [B*T, 3C] qkv view
+int conv_tc_make_map_2d(ConvTensorMap* out, const void* ptr, unsigned long long inner,
+                        unsigned long long outer, int box_inner, int box_outer);
 // fp16 weights [Cout][K] with K = taps*Cin ordered (tap, channel)
 int conv_tc_make_weight_map(ConvTensorMap* out, const void* ptr, int Cout, int K, int BN);
 

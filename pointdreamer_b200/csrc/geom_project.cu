@@ -380,7 +380,7 @@ __device__ __forceinline__ unsigned long long raster_shade_fast(const RasterEdge
 // step), so the work is proportional to the covered area, not to triangles x tile pixels.  Hits go
 // to the shared z-buffer with a 64-bit shared-memory atomicMin on the packed (z, face id) key (the
 // minimum of a set: order independent); then thread = pixel writes all outputs once, coalesced.
-__global__ void __launch_bounds__(RT_W * RT_H)
+__global__ void __launch_bounds__(RT_W * RT_H, 4)  // <= 64 registers: 4+ tiles resident per SM
 raster_tile_kernel(int V, int F, int res, int out_res, int tiles_x, int tiles, RasterWs ws,
                    float* __restrict__ depth, long long* __restrict__ face_idx,
                    uint8_t* __restrict__ mask_cam, uint8_t* __restrict__ mask_out) {

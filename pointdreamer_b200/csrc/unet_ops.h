@@ -44,6 +44,9 @@ int head_launch(const __half* h, const float* stats, const float* gamma, const f
 
 // qkv [B,T,3C] (legacy head-major layout) -> a [B,T,C]; head dim 64
 // prescaled != 0: q and k were already multiplied by 64^-1/4 (fp16) by the qkv conv's epilogue
+// tcgen05 version (attention_tc.cu): T % 128 == 0 and q, k already scaled
+bool attention_tc_ok(int T, int prescaled);
+int attention_tc_launch(const __half* qkv, int B, int T, int heads, __half* out, cudaStream_t stream);
 int attention_launch(const __half* qkv, int B, int T, int heads, int prescaled, __half* out,
                      cudaStream_t stream);
 

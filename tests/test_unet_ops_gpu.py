@@ -156,6 +156,34 @@ def test_attention(cuda, T, heads):
     assert err.max().item() < 4e-3 * max(1.0, a.abs().max().item())
 
 
+@pytest.mark.parametrize("T,heads,B", [(128, 2, 1), (256, 4, 2), (1024, 3, 2)])
+def test_attention_prescaled_tcgen05(cuda, T, heads, B):
+    """pdr_attention_prescaled: q and k arrive already scaled (what the engine's qkv projection
+    emits); T % 128 == 0 runs attention_tc_kernel (tcgen05: S and O in tensor memory, V read as an
+    MN-major operand).  Same reference and the same bound as the mma.sync kernel's test."""
+    g = torch.Generator().manual_seed(9)
+    dh = 64
+    C = heads * dh
+    scale = 1 / math.sqrt(math.sqrt(dh))
+    qkv = h((torch.randn(B, 3 * C, T, generator=g)).to(cuda))  # [B, 3C, T] like the reference
+    q, k, v = qkv.reshape(B * heads, dh * 3, T).split(dh, dim=1)
+    qs, ks = h(q * scale), h(k * scale)
+    pre = torch.cat([qs, ks, v], 1).reshape(B, 3 * C, T)
+    out = torch.empty(B, T, C, device=cuda, dtype=torch.float16)
+    _lib.call("pdr_attention_prescaled", pre.permute(0, 2, 1).contiguous().half(), B, T, heads, out)
+    w = h(torch.einsum("bct,bcs->bts", qs, ks))
+    w = h(torch.softmax(w.float(), dim=-1))
+    a = h(torch.einsum("bts,bcs->bct", w, v)).reshape(B, -1, T)
+    got = out.float().permute(0, 2, 1)
+    err = (got - a).abs()
+    print("attention (prescaled)", T, heads, "max err", err.max().item(), "ref max", a.abs().max().item())
+    assert err.max().item() < 4e-3 * max(1.0, a.abs().max().item())
+    # the raw-input entry point (mma.sync kernel) gives the same tensor up to P rounding flips
+    out2 = torch.empty_like(out)
+    _lib.call("pdr_attention", qkv.permute(0, 2, 1).contiguous().half(), B, T, heads, out2)
+    assert (out.float() - out2.float()).abs().max().item() < 4e-3 * max(1.0, a.abs().max().item())
+
+
 @pytest.mark.parametrize("C,n_out", [(64, 6), (256, 3)])
 def test_head(cuda, C, n_out):
     g = torch.Generator().manual_seed(5)
