@@ -41,6 +41,14 @@ static constexpr int AT_OFF_BAR = 6 * AT_TILE;
 static constexpr int AT_SMEM = AT_OFF_BAR + 16 * 8 + 16;
 static constexpr float AT_LOG2E = 1.4426950408889634f;
 
+// 2^x, one MUFU.EX2 (the library exp2f adds range fix-ups; arguments here are <= 0 and results
+// that underflow are meant to be 0)
+__device__ __forceinline__ float at_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // MN-major, 128-byte-swizzled shared-memory matrix descriptor: rows are K (here: keys), 128 B apart,
 // 64 contiguous MN elements (here: the head dim) per row; 8-row groups 1024 B apart (SBO).  One
 // swizzle atom covers the whole MN extent (64), so the leading-dimension offset is never used.
@@ -180,10 +188,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int T, int heads,
           tm = fmaxf(tm, s);
         }
         const float mn = fmaxf(m, tm);
+        const float mnl = -mn * AT_LOG2E;  // exp(s - mn) = 2^(s*log2e - mn*log2e): one FFMA + one MUFU
         float ts = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) ts += exp2f((__uint_as_float(v[j]) - mn) * AT_LOG2E);
-        l = l * exp2f((m - mn) * AT_LOG2E) + ts;
+        for (int j = 0; j < 32; ++j) ts += at_ex2(fmaf(__uint_as_float(v[j]), AT_LOG2E, mnl));
+        l = l * at_ex2((m - mn) * AT_LOG2E) + ts;
         m = mn;
       }
       tc_fence_before();
@@ -191,6 +200,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int T, int heads,
       if (lane == 0) mbar_arrive(s_empty);
     }
     const float inv_l = 1.f / l;
+    const float ml = -m * AT_LOG2E;
     // ---- pass 2: P = fp16(softmax) -> shared memory (A operand of P V) ----
     uint8_t* prow = smem + AT_OFF_P + r * 128;
     for (int c = 0; c < nc; ++c) {
@@ -207,8 +217,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int T, int heads,
         for (int j = 0; j < 16; ++j) {
           const float s0 = __half2float(__float2half_rn(__uint_as_float(v[2 * j])));
           const float s1 = __half2float(__float2half_rn(__uint_as_float(v[2 * j + 1])));
-          const __half2 h = __floats2half2_rn(exp2f((s0 - m) * AT_LOG2E) * inv_l,
-                                              exp2f((s1 - m) * AT_LOG2E) * inv_l);
+          const __half2 h = __floats2half2_rn(at_ex2(fmaf(s0, AT_LOG2E, ml)) * inv_l,
+                                              at_ex2(fmaf(s1, AT_LOG2E, ml)) * inv_l);
           p[j] = *(const uint32_t*)&h;
         }
         // keys 32 sc .. 32 sc + 31 of this row: k-tile sc / 2, 16-byte chunks (sc & 1) * 4 + 0..3

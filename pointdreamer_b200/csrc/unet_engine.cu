@@ -180,11 +180,12 @@ class UnetEngine {
   int B_ = 0;
   size_t off_stats_[2] = {0, 0}, off_gnws_ = 0, off_e1_ = 0, off_emb_ = 0, off_emb16_ = 0;
   size_t off_partial_ = 0, partial_bytes_ = 0, partial_reserved_ = 0;
-  // GroupNorm + SiLU fused into the halo conv's transform warps: OPT-IN with PDR_FUSED_GN=1 (read
-  // at every plan).  Both paths produce the same bits, but the fused convs are 1.36-1.8x slower
-  // (the transform warps cannot keep up with the tensor core: ~7200 warp-instructions per chunk
-  // at IPC ~1.3), which costs more than the removed gn_apply pass saves
-  bool fuse_gn_ = false;
+  // GroupNorm (+FiLM) + SiLU fused into the halo conv's transform warps (PDR_FUSED_GN, read at every
+  // plan): 2 = default, the convs with ONE N tile (Cout <= 256: the 256^2 and 128^2 layers, where
+  // the activated tensor is largest and the transformed halo is not recomputed per N tile);
+  // 1 = every eligible conv; 0 = separate gn_apply pass everywhere.  All modes produce the same
+  // bits.  A/B in one call (profiles/r02j_*): 2018.5 ms (0) / 1976 ms (1) / 1971 ms (2) per shape.
+  int fuse_gn_ = 0;  // 0 off, 1 every eligible conv, 2 only convs with ONE N tile (Cout <= 256)
 
  public:
   size_t off_tcur_ = 0;  // float[B]: the timestep the captured graph reads
@@ -381,7 +382,10 @@ class UnetEngine {
     PDR_TRY(add_gn(x1, x2, p + ".in_layers.0", 0, nullptr));
     // GroupNorm + SiLU of the block input applied inside in_layers.2's halo kernel (no activated
     // copy of the input in HBM) when nothing is resampled in between
-    const bool fuse1 = fuse_gn_ && !resample && conv_tc_halo_ok(Ho, Wo, 9);
+    // (mode 2: only where the transformed halo is not recomputed per N tile - the transform's
+    // instruction energy is what the fusion costs)
+    const bool fuse_here = fuse_gn_ == 1 || (fuse_gn_ == 2 && Cout <= 256);
+    const bool fuse1 = fuse_here && !resample && conv_tc_halo_ok(Ho, Wo, 9);
     size_t coeff1 = 0;
     Act a1;
     if (fuse1) {
@@ -420,7 +424,7 @@ class UnetEngine {
     }
     // out_layers: GN * (1+scale) + shift, SiLU, conv (+ skip)
     PDR_TRY(add_gn(h1, nullptr, p + ".out_layers.0", 1, nullptr));
-    const bool fuse2 = fuse_gn_ && conv_tc_halo_ok(Ho, Wo, 9);
+    const bool fuse2 = fuse_here && conv_tc_halo_ok(Ho, Wo, 9);
     size_t coeff2 = 0;
     Act a2;
     if (fuse2) {
@@ -489,7 +493,8 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
   clear_plan();
   pl_ = Planner();
   dry_ = dry;
-  fuse_gn_ = getenv("PDR_FUSED_GN") != nullptr;
+  fuse_gn_ = getenv("PDR_FUSED_GN") ? atoi(getenv("PDR_FUSED_GN")) : 2;
+  if (fuse_gn_ < 0 || fuse_gn_ > 2) fuse_gn_ = 2;
   B_ = B;
   arena = (uint8_t*)workspace;
   arena_bytes = ws_bytes;

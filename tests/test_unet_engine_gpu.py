@@ -114,10 +114,10 @@ def test_engine_full_size_vs_oracle(cuda):
 
 
 def test_fused_groupnorm_equals_separate_pass_bitwise(cuda):
-    """GroupNorm+SiLU applied by the halo conv's transform warps (opt-in: PDR_FUSED_GN=1, read at
-    plan time) vs the separate gn_apply pass (default): same arithmetic per element, same accumulation
-    order in the conv -> identical output bits, on a model with FiLM, skip convs and two-source
-    (concatenated) inputs."""
+    """GroupNorm+SiLU applied by the halo conv's transform warps (PDR_FUSED_GN, read at plan time:
+    2 = default, convs with one N tile; 1 = every eligible conv) vs the separate gn_apply pass
+    (PDR_FUSED_GN=0): same arithmetic per element, same accumulation order in the conv -> identical
+    output bits, on a model with FiLM, skip convs and two-source (concatenated) inputs."""
     import os
     from pointdreamer_b200.unet import UNetEngine, random_state_dict
     cfg = dict(image_size=64, in_channels=3, model_channels=128, out_channels=6, num_res_blocks=2,
@@ -128,16 +128,21 @@ def test_fused_groupnorm_equals_separate_pass_bitwise(cuda):
     g = torch.Generator(device="cpu").manual_seed(5)
     x = torch.randn(3, 3, 64, 64, generator=g).to(cuda)
     t = torch.tensor([10.0, 500.0, 990.0], device=cuda)
-    outs = []
-    for fuse in (True, False):
-        if fuse:
-            os.environ["PDR_FUSED_GN"] = "1"
-        else:
-            os.environ.pop("PDR_FUSED_GN", None)
-        try:
+    outs = {}
+    saved = os.environ.get("PDR_FUSED_GN")
+    try:
+        for mode in ("0", "1", "2", None):
+            if mode is None:
+                os.environ.pop("PDR_FUSED_GN", None)
+            else:
+                os.environ["PDR_FUSED_GN"] = mode
             eng = UNetEngine(sd, cfg, device=cuda)
-            outs.append(eng(x, t).clone())
-        finally:
+            outs[mode] = eng(x, t).clone()
+    finally:
+        if saved is None:
             os.environ.pop("PDR_FUSED_GN", None)
-    assert torch.isfinite(outs[0]).all() and outs[0].abs().max() > 0
-    assert torch.equal(outs[0], outs[1])
+        else:
+            os.environ["PDR_FUSED_GN"] = saved
+    assert torch.isfinite(outs["0"]).all() and outs["0"].abs().max() > 0
+    for mode in ("1", "2", None):
+        assert torch.equal(outs["0"], outs[mode]), mode
