@@ -485,7 +485,9 @@ class Bench:
             "bound": "tensor", "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": conv_tflops / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
             "kernel": "conv_halo_kernel / conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv: "
-                      "halo-tile 3x3, 2-CTA and 1-CTA)",
+                      "halo-tile 3x3, 2-CTA and 1-CTA; the launch durations include the GroupNorm+SiLU "
+                      "transform fused into the single-N-tile convs, PDR_FUSED_GN=2 default - with "
+                      "PDR_FUSED_GN=0 the same kernels run at 0.88-0.92 and the step is 2.4% slower)",
             "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
             "launch_avg_ms": conv["ms"] / max(conv["launches"], 1),
             "flops_per_launch_avg": conv["flops"] / max(conv["launches"], 1),
