@@ -241,8 +241,10 @@ class UnetEngine {
     return 0;
   }
 
+  // raw: resampling blocks only - the resampled RAW input (x_upd of ResBlock._forward,
+  // unet.py:241) is written by the same kernel from the same read (no separate resample pass)
   int add_gn_apply(const Act& x1, const Act* x2, const std::string& pname, int which, bool film,
-                   int film_off, bool silu, int resample, const Act& out) {
+                   int film_off, bool silu, int resample, const Act& out, const Act* raw = nullptr) {
     if (dry_) return 0;
     const int C = x1.C + (x2 ? x2->C : 0);
     const float* g = (const float*)find(pname + ".weight", (size_t)C * 4)->ptr;
@@ -257,10 +259,11 @@ class UnetEngine {
     const __half* fl = film ? P<__half>(off_emb16_) : nullptr;
     const int fstride = emb_total_;
     __half* o = P<__half>(out.off);
+    __half* ro = raw ? P<__half>(raw->off) : nullptr;
     ops.cur_cls = PDR_OP_GN_APPLY;
     ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
       return gn_apply_launch(p1, p2, Bn, H, W, C1, C2, st, s1, s2, g, b, fl, fstride, film_off,
-                             silu ? 1 : 0, resample, o, s);
+                             silu ? 1 : 0, resample, o, s, ro);
     });
     return 0;
   }
@@ -387,14 +390,7 @@ class UnetEngine {
     const bool fuse_here = fuse_gn_ == 1 || (fuse_gn_ == 2 && Cout <= 256);
     const bool fuse1 = fuse_here && !resample && conv_tc_halo_ok(Ho, Wo, 9);
     size_t coeff1 = 0;
-    Act a1;
-    if (fuse1) {
-      PDR_TRY(add_gn_coeff(x1, x2, p + ".in_layers.0", 0, false, 0, &coeff1));
-    } else {
-      a1 = new_act(Ho, Wo, Cin);
-      PDR_TRY(add_gn_apply(x1, x2, p + ".in_layers.0", 0, false, 0, true, resample, a1));
-    }
-    Act xr;
+    Act a1, xr;
     bool have_xr = false;
     if (resample) {
       if (x2) {
@@ -403,15 +399,13 @@ class UnetEngine {
       }
       xr = new_act(Ho, Wo, Cin);
       have_xr = true;
-      if (!dry_) {
-        const __half* src = P<__half>(x1.off);
-        __half* dst = P<__half>(xr.off);
-        const int H = x1.H, W = x1.W, Bn = B_;
-        ops.cur_cls = PDR_OP_RESAMPLE;
-        ops.push_back([=](const float*, const float*, float*, int, cudaStream_t s) {
-          return resample_launch(src, Bn, H, W, Cin, resample, dst, s);
-        });
-      }
+    }
+    if (fuse1) {
+      PDR_TRY(add_gn_coeff(x1, x2, p + ".in_layers.0", 0, false, 0, &coeff1));
+    } else {
+      a1 = new_act(Ho, Wo, Cin);
+      PDR_TRY(add_gn_apply(x1, x2, p + ".in_layers.0", 0, false, 0, true, resample, a1,
+                           have_xr ? &xr : nullptr));
     }
     Act h1 = new_act(Ho, Wo, Cout);
     if (fuse1) {

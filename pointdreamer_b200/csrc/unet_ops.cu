@@ -513,6 +513,8 @@ struct GnApplyArgs {
   int film_stride, film_off;
   int silu, resample;
   __half* out;
+  __half* raw_out;       // resample != 0: also emit the resampled RAW input (ResBlock's x_upd,
+                         // unet.py:241) from the same read; same arithmetic as resample_kernel
 };
 
 // thread = fixed 8-channel chunk (affine constants live in registers), loops over pixels of its
@@ -615,6 +617,21 @@ gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         v[u] = __ldg((const uint4*)(src + ((size_t)(2 * yo + (u >> 1)) * W + 2 * xo + (u & 1)) * sstride));
+      if (a.raw_out) {  // AvgPool2d(2) of the raw input, summed in the order of resample_kernel
+        float racc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) racc[j] = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const __half* hh = (const __half*)&v[u];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) racc[j] += h2f(hh[j]);
+        }
+        __align__(16) __half ro[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ro[j] = __float2half_rn(racc[j] * 0.25f);
+        *(uint4*)(a.raw_out + ((size_t)b * Ho * Wo + p) * C + c0) = *(const uint4*)ro;
+      }
       float2 acc[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[j] = make_float2(0.f, 0.f);
@@ -646,6 +663,12 @@ gn_apply_kernel(const GnApplyArgs a, int pix_per_block) {
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         *(uint4*)(dst + ((size_t)(2 * yi + (u >> 1)) * Wo + 2 * xi + (u & 1)) * C) = o;
+      if (a.raw_out) {
+        __half* rdst = a.raw_out + (size_t)b * H * 2 * Wo * C + c0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *(uint4*)(rdst + ((size_t)(2 * yi + (u >> 1)) * Wo + 2 * xi + (u & 1)) * C) = v;
+      }
     }
   }
 }
@@ -702,6 +725,7 @@ int gn_coeff_launch(int B, int H, int W, int C1, int C2, const float* stats, con
   a.sums1 = sums1, a.sums2 = sums2 ? sums2 : sums1;
   a.film = film, a.film_stride = film_stride, a.film_off = film_off;
   a.silu = 1, a.resample = 0, a.out = nullptr;
+  a.raw_out = nullptr;
   gn_coeff_kernel<<<cdiv((long long)B * C, 256), 256, 0, stream>>>(a, coeff);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
@@ -712,9 +736,11 @@ int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int
                     const float* stats, const double* sums1, const double* sums2,
                     const float* gamma, const float* beta,
                     const __half* film, int film_stride, int film_off, int silu, int resample,
-                    __half* out, cudaStream_t stream) {
+                    __half* out, cudaStream_t stream, __half* raw_out) {
   const int C = C1 + C2;
   PDR_CHECK_ARG(C % 32 == 0 && C1 % 8 == 0 && C2 % 8 == 0, "GroupNorm32 apply: bad channels");
+  PDR_CHECK_ARG(raw_out == nullptr || (resample != 0 && C2 == 0),
+                "GroupNorm32 apply: the raw resampled copy needs a single-source resampling call");
   PDR_CHECK_ARG(resample != 1 || (H % 2 == 0 && W % 2 == 0), "avg-pool needs even size");
   GnApplyArgs a;
   a.x1 = x1;
@@ -726,6 +752,7 @@ int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int
   PDR_CHECK_ARG(!sums1 || (C % 256 == 0), "GroupNorm32 apply from sums needs 8-aligned groups");
   a.film = film, a.film_stride = film_stride, a.film_off = film_off;
   a.silu = silu, a.resample = resample, a.out = out;
+  a.raw_out = raw_out;
   const int chunks = C / 8;
   const int threads = chunks >= 256 ? chunks : 256 / chunks * chunks;
   PDR_CHECK_ARG(threads <= 1024, "GroupNorm32 apply: too many channels");

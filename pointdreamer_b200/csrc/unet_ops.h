@@ -31,7 +31,7 @@ int gn_apply_launch(const __half* x1, const __half* x2, int B, int H, int W, int
                     const float* stats, const double* sums1, const double* sums2,
                     const float* gamma, const float* beta,
                     const __half* film, int film_stride, int film_off, int silu, int resample,
-                    __half* out, cudaStream_t stream);
+                    __half* out, cudaStream_t stream, __half* raw_out = nullptr);
 // constants of a GroupNorm32 (+FiLM) applied inside the consuming conv: coeff float4[B][C1+C2]
 int gn_coeff_launch(int B, int H, int W, int C1, int C2, const float* stats, const double* sums1,
                     const double* sums2, const float* gamma, const float* beta, const __half* film,
