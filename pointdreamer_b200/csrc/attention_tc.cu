@@ -15,10 +15,12 @@
 //                          O[128 x 64] += P_c V_c (K = 128 keys: eight tcgen05.mma; V_c is read as an
 //                          MN-major B operand straight from its [key][d] tile - no transpose)
 //   warp 2   TMEM allocator (256 columns: S 128, O 64)
-//   warps 4-7 softmax: tcgen05.ld their row of S, round to fp16; pass 1: online max / sum;
-//            pass 2: P = fp16(exp(s - m) / l) written to shared memory in the K-major 128-byte-swizzled
-//            layout the MMA reads; at the end O -> fp16 -> global.
-// 96 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM overlap each other's MMA,
+//   warps 4-11 softmax (two warps per TMEM lane quadrant, each owning 64 of the chunk's 128 key
+//            columns): tcgen05.ld their row of S, round to fp16; pass 1: online max / sum (the two
+//            halves of a row are merged once, through shared memory); pass 2: P = fp16(exp(s - m) / l)
+//            written to shared memory in the K-major 128-byte-swizzled layout the MMA reads (a thread's
+//            64 columns are exactly one k-tile row); at the end O -> fp16 -> global.
+// 98 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM overlap each other's MMA,
 // TMA and softmax phases, so the per-CTA pipeline itself is strictly sequential (one S buffer, one P
 // buffer) and easy to reason about.
 #include <cuda.h>
@@ -38,7 +40,9 @@ static constexpr int AT_OFF_K = AT_TILE;              // 2 stages
 static constexpr int AT_OFF_V = 3 * AT_TILE;          // 1 stage
 static constexpr int AT_OFF_P = 4 * AT_TILE;          // 128 x 128 fp16 = 2 k-tiles of 16 KB
 static constexpr int AT_OFF_BAR = 6 * AT_TILE;
-static constexpr int AT_SMEM = AT_OFF_BAR + 16 * 8 + 16;
+static constexpr int AT_OFF_ML = AT_OFF_BAR + 16 * 8 + 16;  // float2[2][128]: (m, l) of the two column halves
+static constexpr int AT_SMEM = AT_OFF_ML + 2 * 128 * 8;
+static constexpr int AT_THREADS = 384;
 static constexpr float AT_LOG2E = 1.4426950408889634f;
 
 // 2^x, one MUFU.EX2 (the library exp2f adds range fix-ups; arguments here are <= 0 and results
@@ -61,7 +65,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr) 
   return d;
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int T, int heads,
                     __half* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -95,8 +99,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int T, int heads,
     mbar_init(v_full, 1);
     mbar_init(v_empty, 1);
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);  // one arrive per softmax warp
-    mbar_init(p_full, 4);
+    mbar_init(s_empty, 8);  // one arrive per softmax warp
+    mbar_init(p_full, 8);
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     fence_mbar_init();
@@ -168,24 +172,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int T, int heads,
   } else if (warp >= 4) {
     // ========================================================== softmax ====
     const int q = warp & 3;           // TMEM lane quadrant of this warp
+    const int hf = (warp - 4) >> 2;   // which 64 of the chunk's 128 key columns
     const int r = q * 32 + lane;      // query row of this thread == TMEM lane
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     float m = -INFINITY, l = 0.f;
     uint32_t v[32];
-    // ---- pass 1: row max and sum of exp over the fp16-rounded logits ----
+    // ---- pass 1: row max and sum of exp over the fp16-rounded logits (this thread's columns) ----
     for (int i = 0; i < nc; ++i) {
       mbar_wait(s_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int sc = 0; sc < AT_KC / 32; ++sc) {
+      for (int sc = 2 * hf; sc < 2 * hf + 2; ++sc) {
         tmem_ld_32x32(tmem_s + lane_off + sc * 32, v);
         tmem_ld_wait();
         float tm = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = __half2float(__float2half_rn(__uint_as_float(v[j])));
-          v[j] = __float_as_uint(s);
-          tm = fmaxf(tm, s);
+        for (int j = 0; j < 32; j += 2) {
+          const float2 s2 = __half22float2(
+              __floats2half2_rn(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+          v[j] = __float_as_uint(s2.x);
+          v[j + 1] = __float_as_uint(s2.y);
+          tm = fmaxf(tm, fmaxf(s2.x, s2.y));
         }
         const float mn = fmaxf(m, tm);
         const float mnl = -mn * AT_LOG2E;  // exp(s - mn) = 2^(s*log2e - mn*log2e): one FFMA + one MUFU
@@ -199,33 +206,43 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int T, int heads,
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);
     }
+    // merge the two column halves of every row (the sum is commutative: both threads get the same bits)
+    {
+      float2* ml = (float2*)(smem + AT_OFF_ML);
+      ml[hf * 128 + r] = make_float2(m, l);
+      named_bar_sync(1, 256);
+      const float2 o = ml[(hf ^ 1) * 128 + r];
+      const float mm = fmaxf(m, o.x);
+      const float la = l * at_ex2((m - mm) * AT_LOG2E), lb = o.y * at_ex2((o.x - mm) * AT_LOG2E);
+      l = hf == 0 ? la + lb : lb + la;
+      m = mm;
+    }
     const float inv_l = 1.f / l;
-    const float ml = -m * AT_LOG2E;
+    const float ml2 = -m * AT_LOG2E;
     // ---- pass 2: P = fp16(softmax) -> shared memory (A operand of P V) ----
-    uint8_t* prow = smem + AT_OFF_P + r * 128;
+    uint8_t* prow = smem + AT_OFF_P + hf * AT_TILE + r * 128;  // this thread's 64 keys = k-tile hf
     for (int c = 0; c < nc; ++c) {
       const int i = nc + c;
       mbar_wait(s_full, i & 1);
       mbar_wait(p_empty, (c & 1) ^ 1);  // the MMAs that read the previous P have retired
       tc_fence_after();
 #pragma unroll 1
-      for (int sc = 0; sc < AT_KC / 32; ++sc) {
-        tmem_ld_32x32(tmem_s + lane_off + sc * 32, v);
+      for (int s2i = 0; s2i < 2; ++s2i) {
+        tmem_ld_32x32(tmem_s + lane_off + (2 * hf + s2i) * 32, v);
         tmem_ld_wait();
         uint32_t p[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float s0 = __half2float(__float2half_rn(__uint_as_float(v[2 * j])));
-          const float s1 = __half2float(__float2half_rn(__uint_as_float(v[2 * j + 1])));
-          const __half2 h = __floats2half2_rn(at_ex2(fmaf(s0, AT_LOG2E, ml)) * inv_l,
-                                              at_ex2(fmaf(s1, AT_LOG2E, ml)) * inv_l);
+          const float2 s2 = __half22float2(
+              __floats2half2_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])));
+          const __half2 h = __floats2half2_rn(at_ex2(fmaf(s2.x, AT_LOG2E, ml2)) * inv_l,
+                                              at_ex2(fmaf(s2.y, AT_LOG2E, ml2)) * inv_l);
           p[j] = *(const uint32_t*)&h;
         }
-        // keys 32 sc .. 32 sc + 31 of this row: k-tile sc / 2, 16-byte chunks (sc & 1) * 4 + 0..3
-        uint8_t* dst = prow + (sc >> 1) * AT_TILE;
+        // keys 32 s2i .. 32 s2i + 31 of this thread's k-tile row: 16-byte chunks s2i * 4 + 0..3
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *(uint4*)(dst + ((((sc & 1) * 4 + j) ^ (r & 7)) << 4)) =
+          *(uint4*)(prow + (((s2i * 4 + j) ^ (r & 7)) << 4)) =
               make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
       }
       tc_fence_before();
@@ -236,20 +253,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, int T, int heads,
         mbar_arrive(p_full);
       }
     }
-    // ---- O -> fp16 -> global ----
+    // ---- O -> fp16 -> global (32 of the 64 head-dim columns per thread) ----
     mbar_wait(o_full, 0);
     tc_fence_after();
     const int C = heads * AT_D;
-    __half* orow = out + ((size_t)(row0 + qt * AT_Q + r)) * C + head * AT_D;
-#pragma unroll
-    for (int hc = 0; hc < 2; ++hc) {
-      tmem_ld_32x32(tmem_o + lane_off + hc * 32, v);
+    __half* orow = out + ((size_t)(row0 + qt * AT_Q + r)) * C + head * AT_D + hf * 32;
+    {
+      tmem_ld_32x32(tmem_o + lane_off + hf * 32, v);
       tmem_ld_wait();
       __align__(16) __half o[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) o[j] = __float2half_rn(__uint_as_float(v[j]));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ((uint4*)(orow + hc * 32))[j] = ((const uint4*)o)[j];
+      for (int j = 0; j < 4; ++j) ((uint4*)orow)[j] = ((const uint4*)o)[j];
     }
     tc_fence_before();
   }
@@ -280,7 +296,7 @@ int attention_tc_launch(const __half* qkv, int B, int T, int heads, __half* out,
                                   AT_SMEM + 1024));
     configured = true;
   }
-  attention_tc_kernel<<<dim3(T / AT_Q, heads, B), 256, AT_SMEM + 1024, stream>>>(
+  attention_tc_kernel<<<dim3(T / AT_Q, heads, B), AT_THREADS, AT_SMEM + 1024, stream>>>(
       *(const CUtensorMap*)&tm, T, heads, out);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
