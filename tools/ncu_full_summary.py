@@ -18,9 +18,8 @@ KEYS = ["gpu__time_duration.sum", "sm__throughput.avg.pct_of_peak_sustained_elap
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-tensor_keys = [h for h in hdr if "tensor" in h and "pct_of_peak" in h]
 for r in rows[2:]:
     print(r[ix["Kernel Name"]].split("(")[0])
-    for k in KEYS + [t for t in tensor_keys if t not in KEYS]:
+    for k in KEYS:
         if k in ix and r[ix[k]] not in ("", "n/a"):
             print(f"    {k:86s} {r[ix[k]]:>16s} {units[ix[k]]}")
