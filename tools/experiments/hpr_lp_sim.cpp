@@ -149,5 +149,123 @@ int main(int argc, char** argv) {
     }
     printf("exact (tile-128 neighbour-first, all survivors): nS %d visible %d | checks %lld resolves %lld clips %lld (clips/pt %.0f)\n", nS, vis3, sc.checks, sc.resolves, sc.clips, (double)sc.clips / nS);
   }
+  // exact, order (d): as (c) plus bounding boxes per 128-constraint tile: a tile is skipped in the scan
+  // when no member can violate any lane's optimum, and in a re-solve when no member can move lo or hi
+  {
+    const int TLs[3] = {128, 64, 32};
+    for (int TL : TLs) {
+    std::vector<int> S; for (int i = 0; i < N; ++i) if (surv[i] && !isE[i]) S.push_back(i);
+    auto key = [&](int x) { int cu = std::min(63, std::max(0, (int)((Q[x].x - u0) / (u1 - u0) * 64))); int cv = std::min(63, std::max(0, (int)((Q[x].y - v0) / (v1 - v0) * 64))); return morton(cu, cv); };
+    std::sort(S.begin(), S.end(), [&](int x, int y) { uint32_t a = key(x), b = key(y); return a != b ? a < b : x < y; });
+    const int nS = S.size(), nT = (nS + TL - 1) / TL, PW = 16;
+    struct Bx { double x0, x1, y0, y1, z0, z1; };
+    std::vector<Bx> bx(nT);
+    for (int t = 0; t < nT; ++t) { Bx b{1e300, -1e300, 1e300, -1e300, 1e300, -1e300}; for (int k = t * TL; k < std::min(nS, (t + 1) * TL); ++k) { const P4& p = Q[S[k]]; b.x0 = fmin(b.x0, p.x); b.x1 = fmax(b.x1, p.x); b.y0 = fmin(b.y0, p.y); b.y1 = fmax(b.y1, p.y); b.z0 = fmin(b.z0, p.z); b.z1 = fmax(b.z1, p.z); } bx[t] = b; }
+    const double EPS = 64 * 2.220446049250313e-16;
+    // max over the box of (z - w) - (x - u) a - (y - v) b, plus a rounding margin
+    auto gmax = [&](const Bx& b, const P4& me, double a, double bb, double ma, double mb) {
+      double xs = (a > 0 ? b.x0 : b.x1) - me.x, ys = (bb > 0 ? b.y0 : b.y1) - me.y;
+      double g = (b.z1 - me.z) - xs * a - ys * bb;
+      double mx = fmax(fabs(b.x0 - me.x), fabs(b.x1 - me.x)), my = fmax(fabs(b.y0 - me.y), fabs(b.y1 - me.y));
+      double mag = fmax(fabs(b.z1 - me.z), fabs(b.z0 - me.z)) + mx * ma + my * mb;
+      return g + EPS * mag;
+    };
+    // E sorted by the Morton code of its 64x64 cell, tiles of ET with boxes (used by the re-solves only)
+    const int ET = 32;
+    std::vector<P4> E2 = E; std::sort(E2.begin(), E2.end(), [&](const P4& x, const P4& y) { uint32_t a = key((int)x.w), b = key((int)y.w); return a != b ? a < b : x.w < y.w; });
+    const int nET = (nE + ET - 1) / ET; std::vector<Bx> ebx(nET);
+    for (int t = 0; t < nET; ++t) { Bx b{1e300, -1e300, 1e300, -1e300, 1e300, -1e300}; for (int k = t * ET; k < std::min(nE, (t + 1) * ET); ++k) { const P4& p = E2[k]; b.x0 = fmin(b.x0, p.x); b.x1 = fmax(b.x1, p.x); b.y0 = fmin(b.y0, p.y); b.y1 = fmax(b.y1, p.y); b.z0 = fmin(b.z0, p.z); b.z1 = fmax(b.z1, p.z); } ebx[t] = b; }
+    long long clips = 0, boxt = 0, resolves = 0, checks = 0, tiles_scanned = 0, tiles_skipped = 0, rtiles_done = 0, rtiles_skip = 0, eclips = 0;
+    int vis4 = 0, mism = 0;
+    auto run_warp = [&](const std::vector<int>& pts, int home) {
+      std::vector<int> order; int ta = home, tb = home;
+      for (int step = 0; step < nT; ++step) { int tau; bool right; if (step == 0) { tau = home; right = true; } else { right = (tb < nT) && (ta == 0 || (step & 1)); tau = right ? tb : ta - 1; } order.push_back(tau); if (right) tb = tau + 1; else ta = tau; }
+      const int np = pts.size();
+      std::vector<double> a(np), b(np); std::vector<char> feas(np, 1);
+      for (int l = 0; l < np; ++l) { a[l] = A[pts[l]]; b[l] = B[pts[l]]; }
+      for (int step = 0; step < nT; ++step) {
+        const int tau = order[step]; const Bx& bb = bx[tau];
+        bool need = false;
+        for (int l = 0; l < np; ++l) if (feas[l]) { boxt++; if (gmax(bb, Q[pts[l]], a[l], b[l], fabs(a[l]), fabs(b[l])) > 0) need = true; }
+        if (!need) { tiles_skipped++; continue; }
+        tiles_scanned++;
+        for (int k = tau * TL; k < std::min(nS, (tau + 1) * TL); ++k) {
+          const P4& c = Q[S[k]];
+          for (int l = 0; l < np; ++l) {
+            if (!feas[l]) continue;
+            const P4& me = Q[pts[l]];
+            checks++;
+            if (c.w == me.w) continue;
+            if ((c.x - me.x) * a[l] + (c.y - me.y) * b[l] < c.z - me.z) {
+              resolves++;
+              double nx = c.x - me.x, ny = c.y - me.y, h = c.z - me.z, nn = nx * nx + ny * ny;
+              if (!(nn > 0)) { feas[l] = 0; continue; }
+              double sc = h / nn, p0x = nx * sc, p0y = ny * sc, dx = -ny, dy = nx;
+              double lo = -INFINITY, hi = INFINITY;
+              if (dx != 0) { double t1 = (-BOX - p0x) / dx, t2 = (BOX - p0x) / dx; lo = fmax(lo, fmin(t1, t2)); hi = fmin(hi, fmax(t1, t2)); } else if (fabs(p0x) > BOX) { feas[l] = 0; continue; }
+              if (dy != 0) { double t1 = (-BOX - p0y) / dy, t2 = (BOX - p0y) / dy; lo = fmax(lo, fmin(t1, t2)); hi = fmin(hi, fmax(t1, t2)); } else if (fabs(p0y) > BOX) { feas[l] = 0; continue; }
+              auto clip = [&](const P4& e) {
+                if (e.w == me.w) return;
+                clips++;
+                double ax = e.x - me.x, ay = e.y - me.y, ah = e.z - me.z;
+                double den = ax * dx + ay * dy, rhs = ah - (ax * p0x + ay * p0y);
+                if (den > 0) { if (rhs > lo * den) lo = rhs / den; } else if (den < 0) { if (rhs > hi * den) hi = rhs / den; } else if (rhs > 0) lo = INFINITY;
+              };
+              auto cantouch = [&](const Bx& b2) {
+                if (!(std::isfinite(lo) && std::isfinite(hi))) return true;
+                boxt++;
+                double alo = p0x + lo * dx, blo = p0y + lo * dy, ahi = p0x + hi * dx, bhi = p0y + hi * dy;
+                double g1 = gmax(b2, me, alo, blo, fabs(p0x) + fabs(lo * dx), fabs(p0y) + fabs(lo * dy));
+                double g2 = gmax(b2, me, ahi, bhi, fabs(p0x) + fabs(hi * dx), fabs(p0y) + fabs(hi * dy));
+                return !(g1 <= 0 && g2 <= 0);
+              };
+              // current tile prefix first, then the earlier tiles (nearest first), then the E tiles
+              for (int kk = tau * TL; kk < k; ++kk) clip(Q[S[kk]]);
+              for (int s2 = 0; s2 < step; ++s2) {
+                const int t2 = order[s2];
+                if (!cantouch(bx[t2])) { rtiles_skip++; continue; }
+                rtiles_done++;
+                for (int kk = t2 * TL; kk < std::min(nS, (t2 + 1) * TL); ++kk) clip(Q[S[kk]]);
+              }
+              for (int t2 = 0; t2 < nET; ++t2) {
+                if (!cantouch(ebx[t2])) continue;
+                for (int kk = t2 * ET; kk < std::min(nE, (t2 + 1) * ET); ++kk) { long long c0 = clips; clip(E2[kk]); eclips += clips - c0; }
+              }
+              for (int s2 = 0; s2 < 0; ++s2) {
+                const int t2 = order[s2]; const Bx& b2 = bx[t2];
+                const int kend = s2 == step ? k : std::min(nS, (t2 + 1) * TL);
+                bool skip = false;
+                if (std::isfinite(lo) && std::isfinite(hi)) {
+                  boxt++;
+                  double alo = p0x + lo * dx, blo = p0y + lo * dy, ahi = p0x + hi * dx, bhi = p0y + hi * dy;
+                  double g1 = gmax(b2, me, alo, blo, fabs(p0x) + fabs(lo * dx), fabs(p0y) + fabs(lo * dy));
+                  double g2 = gmax(b2, me, ahi, bhi, fabs(p0x) + fabs(hi * dx), fabs(p0y) + fabs(hi * dy));
+                  skip = g1 <= 0 && g2 <= 0;
+                }
+                if (skip) { rtiles_skip++; continue; }
+                rtiles_done++;
+                for (int kk = t2 * TL; kk < kend; ++kk) clip(Q[S[kk]]);
+              }
+              if (!(lo <= hi)) { feas[l] = 0; continue; }
+              double tt = (1.0 * dx + 0.5 * dy > 0) ? hi : lo;
+              a[l] = p0x + tt * dx; b[l] = p0y + tt * dy;
+            }
+          }
+        }
+      }
+      for (int l = 0; l < np; ++l) { vis4 += feas[l]; if ((bool)feas[l] != (bool)resA[pts[l]]) mism++; }
+    };
+    for (int s0 = 0; s0 < nS; s0 += PW) { std::vector<int> pts; for (int k = s0; k < std::min(nS, s0 + PW); ++k) pts.push_back(S[k]); run_warp(pts, s0 / TL); }
+    std::vector<int> Es; for (int k = 0; k < nE; ++k) if (surv[(int)E[k].w]) Es.push_back((int)E[k].w);
+    for (size_t e0 = 0; e0 < Es.size(); e0 += PW) {
+      uint32_t kk = key(Es[e0]);
+      int pos = std::lower_bound(S.begin(), S.end(), kk, [&](int x, uint32_t v) { return key(x) < v; }) - S.begin();
+      std::vector<int> pts; for (size_t k = e0; k < std::min(Es.size(), e0 + PW); ++k) pts.push_back(Es[k]);
+      run_warp(pts, std::min(nT - 1, pos / TL));
+    }
+    printf("exact (boxes, tile %d): visible %d mismatches %d | checks %lld resolves %lld clips %lld (clips/pt %.0f) (E part %lld) box tests %lld | scan tiles %lld scanned %lld skipped | resolve tiles %lld done %lld skipped\n",
+           TL, vis4, mism, checks, resolves, clips, (double)clips / nC, eclips, boxt, tiles_scanned, tiles_skipped, rtiles_done, rtiles_skip);
+    }
+  }
   return 0;
 }
