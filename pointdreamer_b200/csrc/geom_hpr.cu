@@ -652,14 +652,22 @@ __device__ __forceinline__ void hpr_resolve_tiles(const HprSeq& sq_, const doubl
       }
       unsigned m = __ballot_sync(0xffffffffu, need);
       if (!m) continue;
-      while (m) {
-        const int j = __ffs(m) - 1;
+      while (m) {  // two tiles per round: four loads in flight per lane
+        const int j0 = __ffs(m) - 1;
         m &= m - 1;
-        const int k0 = __shfl_sync(0xffffffffu, tl, j) * HPR_ST, k1 = min(sq_.nS, k0 + HPR_ST);
-        const double4 c0_ = k0 + lane < k1 ? sq_.S[k0 + lane] : make_double4(0, 0, 0, ln.iL);
-        const double4 c1_ = k0 + lane + 32 < k1 ? sq_.S[k0 + lane + 32] : make_double4(0, 0, 0, ln.iL);
+        const int j1 = m ? __ffs(m) - 1 : j0;
+        m &= m - 1;  // (0 & anything = 0)
+        const int k0 = __shfl_sync(0xffffffffu, tl, j0) * HPR_ST, k1 = min(sq_.nS, k0 + HPR_ST);
+        const int k2 = __shfl_sync(0xffffffffu, tl, j1) * HPR_ST, k3 = j1 != j0 ? min(sq_.nS, k2 + HPR_ST) : 0;
+        const double4 dummy = make_double4(0.0, 0.0, 0.0, ln.iL);
+        const double4 c0_ = k0 + lane < k1 ? sq_.S[k0 + lane] : dummy;
+        const double4 c1_ = k0 + lane + 32 < k1 ? sq_.S[k0 + lane + 32] : dummy;
+        const double4 c2_ = k2 + lane < k3 ? sq_.S[k2 + lane] : dummy;
+        const double4 c3_ = k2 + lane + 32 < k3 ? sq_.S[k2 + lane + 32] : dummy;
         hpr_line_clip(ln, c0_);
         hpr_line_clip(ln, c1_);
+        hpr_line_clip(ln, c2_);
+        hpr_line_clip(ln, c3_);
       }
       empty = hpr_line_reduce(ln);
     }
@@ -669,11 +677,16 @@ __device__ __forceinline__ void hpr_resolve_tiles(const HprSeq& sq_, const doubl
       const bool need = e < HPR_NET && sq_.ecnt[e] > 0 && hpr_line_box(ln, sq_.ebox + (size_t)e * 6);
       unsigned m = __ballot_sync(0xffffffffu, need);
       if (!m) continue;
-      while (m) {
-        const int j = __ffs(m) - 1;
+      while (m) {  // two blocks per round
+        const int ej0 = e0 + __ffs(m) - 1;
         m &= m - 1;
-        const int ej = e0 + j;
-        if (lane < sq_.ecnt[ej]) hpr_line_clip(ln, sq_.E2[(size_t)ej * 32 + lane]);
+        const int ej1 = m ? e0 + __ffs(m) - 1 : -1;
+        m &= m - 1;
+        const double4 dummy = make_double4(0.0, 0.0, 0.0, ln.iL);
+        const double4 c0_ = lane < sq_.ecnt[ej0] ? sq_.E2[ej0 * 32 + lane] : dummy;
+        const double4 c1_ = ej1 >= 0 && lane < sq_.ecnt[ej1] ? sq_.E2[ej1 * 32 + lane] : dummy;
+        hpr_line_clip(ln, c0_);
+        hpr_line_clip(ln, c1_);
       }
       empty = hpr_line_reduce(ln);
     }
@@ -714,30 +727,52 @@ __device__ __forceinline__ void hpr_resolve_tiles(const HprSeq& sq_, const doubl
   }
 }
 
-// EXACT: one warp per block (warps re-solve at very different times, so nothing may couple them) and
-// only HPR_EXACT_POINTS points per warp: the warp-wide re-solves of its points are serialised, so
-// fewer points per warp (more warps in flight) shortens every warp's critical path.  Blocks
-// [0, 2 NET) own the surviving extremes (two half blocks of E2 each), the others 16 consecutive
-// survivors of S.
-static constexpr int HPR_EXACT_POINTS = 16;
-__global__ void __launch_bounds__(32)
+// EXACT: HPR_EXACT_WARPS independent warps per block (nothing couples them after the start: they
+// re-solve at very different times) sharing the view's extremes E2 + boxes in shared memory - a
+// re-solve touches a dozen E blocks one after the other, so their latency is its critical path.
+// HPR_EXACT_POINTS points per warp (the other lanes only help in the re-solves, which are warp wide
+// and serialised).  Warps [0, 2 NET) of a view own the surviving extremes (two half blocks of E2
+// each), the others 16 consecutive survivors of S.  ncu (profiles/r02q_*): fixed-latency fp64
+// dependency waits dominate (3 of 7 stall cycles per issue), loads do not.
+static constexpr int HPR_EXACT_POINTS = 16;  // measured: 8 -> -2 % / -6 %, 4 -> -12 % / -22 % (2 / 8 views)
+static constexpr int HPR_EXACT_WARPS = 8;    // 126 registers, no spills; 10 warps (96 registers, spills) was slower
+static constexpr int HPR_EXACT_SMEM_E = HPR_NET * 32 * 32 + HPR_NET * 6 * 8 + 256;  // E2, ebox, ecnt
+static constexpr int HPR_EXACT_SMEM_W = HPR_ST * 32 + 32 * 6 * 8;                   // per warp: tile, boxes
+static constexpr int HPR_EXACT_SMEM = HPR_EXACT_SMEM_E + HPR_EXACT_WARPS * HPR_EXACT_SMEM_W;
+static_assert(HPR_NET * 4 <= 256, "ecnt region");
+__global__ void __launch_bounds__(32 * HPR_EXACT_WARPS, 2)
 hpr_exact_kernel(int N, HprWs ws, uint8_t* __restrict__ vis) {
-  __shared__ double4 sq[HPR_ST];
-  __shared__ double sbx[32 * 6];
-  const int v = blockIdx.y, lane = threadIdx.x;
+  extern __shared__ __align__(32) uint8_t hpr_smem[];
+  double4* sE2 = (double4*)hpr_smem;
+  double* sebox = (double*)(hpr_smem + HPR_NET * 32 * 32);
+  int* secnt = (int*)(hpr_smem + HPR_NET * 32 * 32 + HPR_NET * 6 * 8);
+  const int v = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double4* sq = (double4*)(hpr_smem + HPR_EXACT_SMEM_E + warp * HPR_EXACT_SMEM_W);
+  double* sbx = (double*)(sq + HPR_ST);
   HprSeq seq;
   seq.nS = ws.nS[v];
   seq.nT = hpr_tiles_dev(seq.nS);
+  // warps past the last point of the view: the whole block leaves before the barrier
+  constexpr int EW = 32 / HPR_EXACT_POINTS;  // warps per E block
+  if (blockIdx.x * HPR_EXACT_WARPS >= EW * HPR_NET + (seq.nS + HPR_EXACT_POINTS - 1) / HPR_EXACT_POINTS)
+    return;
+  for (int k = threadIdx.x; k < HPR_NET * 32; k += blockDim.x)
+    sE2[k] = ws.E2[(size_t)v * HPR_NET * 32 + k];
+  for (int k = threadIdx.x; k < HPR_NET * 6; k += blockDim.x)
+    sebox[k] = ws.ebox[(size_t)v * HPR_NET * 6 + k];
+  for (int k = threadIdx.x; k < HPR_NET; k += blockDim.x) secnt[k] = ws.ecnt[v * HPR_NET + k];
+  __syncthreads();  // the only block-wide synchronisation
+  const int vb = blockIdx.x * HPR_EXACT_WARPS + warp;
   seq.S = ws.S + (size_t)v * N;
   seq.sbox = ws.sbox + (size_t)v * hpr_tiles_dev(N) * 6;
-  seq.E2 = ws.E2 + (size_t)v * HPR_NET * 32;
-  seq.ebox = ws.ebox + (size_t)v * HPR_NET * 6;
-  seq.ecnt = ws.ecnt + v * HPR_NET;
+  seq.E2 = sE2;
+  seq.ebox = sebox;
+  seq.ecnt = secnt;
   double4 me = make_double4(0.0, 0.0, 0.0, -1.0);
   double2 ab0 = make_double2(0.0, 0.0);
   bool active = false;
-  if (blockIdx.x < 2 * HPR_NET) {
-    const int t = blockIdx.x >> 1, r0 = (blockIdx.x & 1) * HPR_EXACT_POINTS;
+  if (vb < EW * HPR_NET) {
+    const int t = vb / EW, r0 = (vb % EW) * HPR_EXACT_POINTS;
     const int cnt = seq.ecnt[t];
     if (r0 >= cnt) return;
     if (lane < HPR_EXACT_POINTS && r0 + lane < cnt) {
@@ -749,7 +784,7 @@ hpr_exact_kernel(int N, HprWs ws, uint8_t* __restrict__ vis) {
     const int first = (int)seq.E2[t * 32 + r0].w;
     seq.home = min(seq.nT - 1, ws.celloffs[v * (HPR_M2 + 1) + ws.mcell[(size_t)v * N + first]] / HPR_ST);
   } else {
-    const int p0 = (blockIdx.x - 2 * HPR_NET) * HPR_EXACT_POINTS;
+    const int p0 = (vb - EW * HPR_NET) * HPR_EXACT_POINTS;
     if (p0 >= seq.nS) return;
     if (lane < HPR_EXACT_POINTS && p0 + lane < seq.nS) {
       me = seq.S[p0 + lane];
@@ -779,14 +814,28 @@ hpr_exact_kernel(int N, HprWs ws, uint8_t* __restrict__ vis) {
       __syncwarp();
       for (int t = lane; t < cnt; t += 32) sq[t] = seq.S[k0 + t];
       __syncwarp();
+      // Pre-test of the scan: constraint j cuts the optimum off iff  z_j - x_j a - y_j b  exceeds the
+      // same expression of the lane's own point.  Evaluated in that form (two FMAs per constraint
+      // instead of the difference form below) against a threshold lowered by a rounding margin
+      // taken from the tile's box, it can only err towards "look again": the decision itself is
+      // always taken by the difference form.
+      const double* bx = sbx + (s - s0) * 6;
+      const double zm = fmax(fabs(bx[4]), fabs(bx[5])) + fabs(me.z);
+      const double xm = fmax(fabs(bx[0]), fabs(bx[1])) + fabs(me.x);
+      const double ym = fmax(fabs(bx[2]), fabs(bx[3])) + fabs(me.y);
+      auto threshold = [&]() {
+        return feasible ? fma(-me.y, b, fma(-me.x, a, me.z)) - HPR_EPS * (zm + xm * fabs(a) + ym * fabs(b))
+                        : INFINITY;
+      };
+      double thr = threshold();
       for (int t0 = 0; t0 < cnt; t0 += 4) {
-        // fast path: none of the next four constraints cuts off any lane's optimum
+        // fast path: none of the next four constraints can cut off any lane's optimum
         bool any = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (t0 + j < cnt) {
-            const double4 cj = sq[t0 + j];
-            any |= feasible && cj.w != me.w && ((cj.x - me.x) * a + (cj.y - me.y) * b < cj.z - me.z);
+            const double2 xy = *reinterpret_cast<const double2*>(&sq[t0 + j]);
+            any |= fma(-xy.y, b, fma(-xy.x, a, sq[t0 + j].z)) > thr;
           }
         }
         if (!__any_sync(0xffffffffu, any)) continue;
@@ -801,6 +850,7 @@ hpr_exact_kernel(int N, HprWs ws, uint8_t* __restrict__ vis) {
             hpr_resolve_tiles(seq, sq, t, s, cj, L, lane, me, a, b, feasible);
           }
         }
+        thr = threshold();  // (a, b) or feasible may have changed
       }
     }
   }
@@ -816,6 +866,8 @@ int hpr_launch(const float* points, int N, int V, const double* frames_dev, doub
   if (!configured) {
     PDR_CUDA(cudaFuncSetAttribute(hpr_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   HPR_G2 * (int)sizeof(double4)));
+    PDR_CUDA(cudaFuncSetAttribute(hpr_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  HPR_EXACT_SMEM));
     configured = true;
   }
   PDR_CUDA(cudaMemsetAsync(ws.isE, 0, (size_t)V * N, stream));
@@ -845,7 +897,9 @@ int hpr_launch(const float* points, int N, int V, const double* frames_dev, doub
   PDR_COUNT_LAUNCH();
   hpr_tilebox_kernel<<<dim3(cdiv(hpr_tiles(N), 8), V), 256, 0, stream>>>(N, ws);
   PDR_COUNT_LAUNCH();
-  hpr_exact_kernel<<<dim3(2 * HPR_NET + cdiv(N, HPR_EXACT_POINTS), V), 32, 0, stream>>>(N, ws, vis);
+  const int exact_warps = (32 / HPR_EXACT_POINTS) * HPR_NET + cdiv(N, HPR_EXACT_POINTS);
+  hpr_exact_kernel<<<dim3(cdiv(exact_warps, HPR_EXACT_WARPS), V), 32 * HPR_EXACT_WARPS, HPR_EXACT_SMEM,
+                     stream>>>(N, ws, vis);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;
