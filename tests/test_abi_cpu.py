@@ -114,3 +114,26 @@ def test_texture_psnr_metric():
     atlas = np.linspace(-0.1, 1.1, 8 * 8 * 3, dtype=np.float32).reshape(8, 8, 3)
     q = metrics.atlas_to_uint8(atlas)
     assert q.dtype == np.uint8 and q[-1, 0, 0] == 0 and q[0, -1, -1] == 255
+
+
+def test_workspace_queries_are_host_functions(lib):
+    """The *_workspace_bytes entry points are pure host code: callable without a GPU, growing with the
+    problem, and large enough for the arrays pdr.h says they carve (the hidden-point-removal one holds
+    three [V, N] double4 arrays - points, sorted survivors - two [V, N] double2 arrays and the sort
+    buckets)."""
+    for name in ("pdr_hidden_point_removal_workspace_bytes", "pdr_rasterize_workspace_bytes",
+                 "pdr_sparse_images_workspace_bytes", "pdr_nearest_fill_workspace_bytes",
+                 "pdr_unproject_workspace_bytes"):
+        getattr(lib, name).restype = ctypes.c_size_t
+    V, N = 8, 30000
+    hpr = lib.pdr_hidden_point_removal_workspace_bytes(V, N)
+    assert hpr >= V * N * (2 * 32 + 2 * 16 + 4 + 2 + 2)
+    assert hpr < 64 << 20  # a production call stays a small slice of HBM
+    assert lib.pdr_hidden_point_removal_workspace_bytes(V, 2 * N) > hpr
+    assert lib.pdr_hidden_point_removal_workspace_bytes(2 * V, N) > hpr
+    assert lib.pdr_hidden_point_removal_workspace_bytes(1, 1) % 256 == 0
+    r = lib.pdr_rasterize_workspace_bytes(8, 20000, 512)
+    assert r > 0 and lib.pdr_rasterize_workspace_bytes(8, 40000, 512) > r
+    assert lib.pdr_nearest_fill_workspace_bytes(1, 1024, 1024) >= 1024 * 1024 * 2
+    assert lib.pdr_sparse_images_workspace_bytes(8, 256) > 0
+    assert lib.pdr_unproject_workspace_bytes(1024, 1) > 0
