@@ -1,5 +1,7 @@
 #!/bin/bash
 # HPR exact pass: points per warp A/B (16 / 8 / 4), parity per variant, one full ncu capture with source counters
+# NOTE: the PDR_HPR_* environment switch used below existed only in the experimental build this job measured
+# (results: profiles/r02u_filter_experiment.md); the committed kernels ignore it.
 mkdir -p gpurun_out
 for p in 16 8 4; do
 PDR_HPR_POINTS=$p timeout 600 python -m pytest tests/test_hpr_gpu.py tests/test_production_goldens_gpu.py \

@@ -1,5 +1,7 @@
 #!/bin/bash
 # pruned HPR filter: points per warp 8 / 16 / 32
+# NOTE: the PDR_HPR_* environment switch used below existed only in the experimental build this job measured
+# (results: profiles/r02u_filter_experiment.md); the committed kernels ignore it.
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_hpr_gpu.py tests/test_production_goldens_gpu.py tests/test_geometry_gpu.py \
     -q -p no:cacheprovider > gpurun_out/r02u_pytest.log 2>&1

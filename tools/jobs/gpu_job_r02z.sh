@@ -1,5 +1,7 @@
 #!/bin/bash
 # HPR filter grid size 40 / 32 / 24: parity per variant, configs[0] at 2 and 8 views, kernel times, configs[1] project stage
+# NOTE: the PDR_HPR_* environment switch used below existed only in the experimental build this job measured
+# (results: profiles/r02u_filter_experiment.md); the committed kernels ignore it.
 mkdir -p gpurun_out
 for g in 40 32 24; do
 PDR_HPR_GRID=$g timeout 600 python -m pytest tests/test_hpr_gpu.py tests/test_production_goldens_gpu.py \
