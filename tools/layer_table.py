@@ -58,6 +58,7 @@ def layers():
 
 
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if not l.startswith("==")) if len(r) > 10 and r[0].isdigit()]
+rows = [r for r in rows if r[-3] == "gpu__time_duration.sum"]  # lists with DRAM metrics hold three rows per launch
 heads = [i for i, r in enumerate(rows) if "head_kernel" in r[4]]
 # a bench.py launch list holds several forwards delimited by head_kernel launches; a conv-only
 # list (ncu -k regex:conv..., one forward of tools/bench_unet.py) is taken whole
