@@ -179,6 +179,7 @@ class UnetEngine {
   bool dry_ = true;
   int B_ = 0;
   size_t off_stats_[2] = {0, 0}, off_gnws_ = 0, off_e1_ = 0, off_emb_ = 0, off_emb16_ = 0;
+  size_t off_embcache_ = 0, off_embmeta_ = 0;  // timestep-embedding cache (unet_ops.h)
   size_t off_partial_ = 0, partial_bytes_ = 0, partial_reserved_ = 0;
   // GroupNorm (+FiLM) + SiLU fused into the halo conv's transform warps (PDR_FUSED_GN, read at every
   // plan): 2 = default, the convs with ONE N tile (Cout <= 256: the 256^2 and 128^2 layers, where
@@ -543,6 +544,9 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
   off_e1_ = pl_.alloc((size_t)B * ted * 4);
   off_emb_ = pl_.alloc((size_t)B * ted * 4);
   off_emb16_ = pl_.alloc((size_t)B * emb_total_ * 2);
+  off_embcache_ = pl_.alloc((size_t)EMB_CACHE_SLOTS * emb_total_ * 2);
+  off_embmeta_ = pl_.alloc(sizeof(EmbCacheMeta));
+  if (!dry_) PDR_CUDA(cudaMemset(arena + off_embmeta_, 0, sizeof(EmbCacheMeta)));  // empty cache
 
   // ---- time embedding + all emb_layers (fp32) ----
   {
@@ -558,14 +562,20 @@ int UnetEngine::plan(int B, void* workspace, size_t ws_bytes, bool dry, size_t* 
       float* emb = P<float>(off_emb_);
       __half* e16 = P<__half>(off_emb16_);
       const int etot = emb_total_;
+      __half* cache = P<__half>(off_embcache_);
+      EmbCacheMeta* meta = P<EmbCacheMeta>(off_embmeta_);
+      // PDR_NO_EMB_CACHE (read at every plan): A/B switch, every forward recomputes the embeddings
+      const int cache_on = getenv("PDR_NO_EMB_CACHE") == nullptr;
       ops.cur_cls = PDR_OP_LINEAR;
       ops.push_back([=](const float*, const float* t, float*, int, cudaStream_t s) {
+        PDR_TRY(emb_cache_lookup_launch(t, B, meta, cache_on, s));
         PDR_TRY(linear_launch(t, (const float*)w0->ptr, (const float*)b0->ptr, B, mc, ted, 2, e1,
-                              nullptr, s));
+                              nullptr, s, &meta->hit));
         PDR_TRY(linear_launch(e1, (const float*)w2->ptr, (const float*)b2->ptr, B, ted, ted, 1,
-                              emb, nullptr, s));
-        return linear_launch(emb, (const float*)we->ptr, (const float*)be->ptr, B, ted, etot, 1,
-                             nullptr, e16, s);
+                              emb, nullptr, s, &meta->hit));
+        PDR_TRY(linear_launch(emb, (const float*)we->ptr, (const float*)be->ptr, B, ted, etot, 1,
+                              nullptr, e16, s, &meta->hit));
+        return emb_cache_finish_launch(e16, B, etot, cache, meta, t, s);
       });
     }
   }

@@ -27,8 +27,10 @@ __device__ __forceinline__ float round_h(float x) { return __half2float(__float2
 // mode_out: 0 fp32, 1 fp32 SiLU(out)... only 0 used; out16 != null additionally stores fp16.
 __global__ void linear_kernel(const float* __restrict__ in, const float* __restrict__ W,
                               const float* __restrict__ bias, int B, int K, int N, int mode_in,
-                              float* __restrict__ out, __half* __restrict__ out16) {
+                              float* __restrict__ out, __half* __restrict__ out16,
+                              const int* __restrict__ skip) {
   extern __shared__ float s_in[];  // [bchunk<=8][K]
+  if (skip && *skip >= 0) return;  // embedding cache hit: the result is already known
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps = blockDim.x >> 5;
   for (int b0 = 0; b0 < B; b0 += 8) {
@@ -100,7 +102,7 @@ __global__ void linear_kernel(const float* __restrict__ in, const float* __restr
 }
 
 int linear_launch(const float* in, const float* W, const float* bias, int B, int K, int N,
-                  int mode_in, float* out, __half* out16, cudaStream_t stream) {
+                  int mode_in, float* out, __half* out16, cudaStream_t stream, const int* skip) {
   PDR_CHECK_ARG(K % 4 == 0 && K <= 4096, "linear: K=%d must be a multiple of 4 and <= 4096", K);
   const int threads = 256;
   const int nbk = B < 8 ? B : 8;
@@ -113,7 +115,65 @@ int linear_launch(const float* in, const float* W, const float* bias, int B, int
   }
   int grid = cdiv(N, (threads / 32) * 4);
   if (grid > 148 * 8) grid = 148 * 8;
-  linear_kernel<<<grid, threads, smem, stream>>>(in, W, bias, B, K, N, mode_in, out, out16);
+  linear_kernel<<<grid, threads, smem, stream>>>(in, W, bias, B, K, N, mode_in, out, out16, skip);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------- timestep-embedding cache ----
+__global__ void __launch_bounds__(32)
+emb_cache_lookup_kernel(const float* __restrict__ t, int B, EmbCacheMeta* __restrict__ m, int enabled) {
+  const int lane = threadIdx.x;
+  const unsigned t0 = __float_as_uint(t[0]);
+  bool same = true;
+  for (int b = lane; b < B; b += 32) same = same && __float_as_uint(t[b]) == t0;
+  same = __all_sync(0xffffffffu, same) && enabled != 0;
+  int hit = -1;
+  const int n = m->n;
+  if (same)
+    for (int k = lane; k < n; k += 32)
+      if (__float_as_uint(m->t[k]) == t0) hit = k;
+  for (int o = 16; o > 0; o >>= 1) hit = max(hit, __shfl_xor_sync(0xffffffffu, hit, o));
+  if (lane == 0) {
+    m->hit = hit;
+    m->store = (hit < 0 && same && n < EMB_CACHE_SLOTS) ? n : -1;
+  }
+}
+
+__global__ void emb_cache_finish_kernel(__half* __restrict__ emb16, int B, int etot,
+                                        __half* __restrict__ cache, EmbCacheMeta* __restrict__ m,
+                                        const float* __restrict__ t) {
+  const int hit = m->hit, store = m->store;  // written by the lookup launch only
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte piece of a row
+  const int pieces = etot / 8;
+  if (hit >= 0) {
+    if (i < pieces) {
+      const uint4 v = reinterpret_cast<const uint4*>(cache + (size_t)hit * etot)[i];
+      for (int b = 0; b < B; ++b) reinterpret_cast<uint4*>(emb16 + (size_t)b * etot)[i] = v;
+    }
+  } else if (store >= 0) {
+    if (i < pieces)
+      reinterpret_cast<uint4*>(cache + (size_t)store * etot)[i] = reinterpret_cast<const uint4*>(emb16)[i];
+    if (i == 0) {  // visible to the next lookup launch (stream order)
+      m->t[store] = t[0];
+      m->n = store + 1;
+    }
+  }
+}
+
+int emb_cache_lookup_launch(const float* t, int B, EmbCacheMeta* meta, int enabled,
+                            cudaStream_t stream) {
+  emb_cache_lookup_kernel<<<1, 32, 0, stream>>>(t, B, meta, enabled);
+  PDR_COUNT_LAUNCH();
+  PDR_LAUNCH_CHECK();
+  return 0;
+}
+
+int emb_cache_finish_launch(__half* emb16, int B, int etot, __half* cache, EmbCacheMeta* meta,
+                            const float* t, cudaStream_t stream) {
+  PDR_CHECK_ARG(etot % 8 == 0, "embedding cache: row length %d must be a multiple of 8", etot);
+  emb_cache_finish_kernel<<<cdiv(etot / 8, 256), 256, 0, stream>>>(emb16, B, etot, cache, meta, t);
   PDR_COUNT_LAUNCH();
   PDR_LAUNCH_CHECK();
   return 0;

@@ -8,8 +8,27 @@
 namespace pdr {
 
 // out[b][n] = bias[n] + sum_k f(in[b][k]) W[n][k]; mode_in 0 identity, 1 SiLU, 2 timestep embedding
+// skip: optional device flag; the launch does nothing when *skip >= 0 (embedding cache hit)
 int linear_launch(const float* in, const float* W, const float* bias, int B, int K, int N,
-                  int mode_in, float* out, __half* out16, cudaStream_t stream);
+                  int mode_in, float* out, __half* out16, cudaStream_t stream,
+                  const int* skip = nullptr);
+
+// Timestep-embedding cache.  The FiLM vectors of all ResBlocks (emb16 [B][etot] fp16) are a pure
+// function of (weights, t); a sampler visits the same timesteps for every shape.  The cache lives in
+// device memory and is looked up ON the device (no host knowledge of t, graph-capturable):
+//   lookup: all B timesteps equal and cached -> meta.hit = slot, else -1 (and meta.store = a free
+//           slot or -1);  the three embedding linears are launched with skip = &meta.hit;
+//   finish: hit -> broadcast the cached row to the B rows of emb16; store -> keep row 0.
+// Cached rows are the bits a recomputation would produce (every row is computed independently).
+static constexpr int EMB_CACHE_SLOTS = 128;
+struct EmbCacheMeta {
+  float t[EMB_CACHE_SLOTS];
+  int n, hit, store, pad;
+};
+int emb_cache_lookup_launch(const float* t, int B, EmbCacheMeta* meta, int enabled,
+                            cudaStream_t stream);
+int emb_cache_finish_launch(__half* emb16, int B, int etot, __half* cache, EmbCacheMeta* meta,
+                            const float* t, cudaStream_t stream);
 
 int stem_conv_launch(const float* x, const __half* w, const float* bias, int B, int H, int W,
                      int C, __half* out, cudaStream_t stream);

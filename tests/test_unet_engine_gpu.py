@@ -146,3 +146,36 @@ def test_fused_groupnorm_equals_separate_pass_bitwise(cuda):
     assert torch.isfinite(outs["0"]).all() and outs["0"].abs().max() > 0
     for mode in ("1", "2", None):
         assert torch.equal(outs["0"], outs[mode]), mode
+
+
+def test_timestep_embedding_cache_is_invisible(cuda, monkeypatch):
+    """The FiLM vectors are cached per timestep on the device (unet_ops.h): a forward that hits the
+    cache, one that misses, one that cannot use it (per-sample timesteps) and an engine with the cache
+    switched off all produce the same bits; more timesteps than slots keep working."""
+    from pointdreamer_b200.unet import UNetEngine
+    sd = ounet.synthetic_state_dict(SMALL, seed=21)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 3, 64, 64, generator=gen).to(cuda)
+    x2 = torch.randn(4, 3, 64, 64, generator=gen).to(cuda)
+    eng = UNetEngine(sd, SMALL, device=cuda)
+    monkeypatch.setenv("PDR_NO_EMB_CACHE", "1")
+    plain = UNetEngine(sd, SMALL, device=cuda)
+    plain.plan(4)  # the switch is read when the engine is planned
+    monkeypatch.delenv("PDR_NO_EMB_CACHE")
+
+    def fwd(e, xx, tt):
+        return e(xx, torch.tensor(tt, device=cuda)).cpu().numpy()
+
+    ref_a = fwd(plain, x, [500.0] * 4)
+    ref_b = fwd(plain, x2, [500.0] * 4)
+    ref_c = fwd(plain, x, [500.0, 10.0, 500.0, 990.0])
+    assert np.array_equal(fwd(eng, x, [500.0] * 4), ref_a)   # miss: computed and stored
+    assert np.array_equal(fwd(eng, x2, [500.0] * 4), ref_b)  # hit: row broadcast from the cache
+    assert np.array_equal(fwd(eng, x, [500.0, 10.0, 500.0, 990.0]), ref_c)  # mixed: bypass
+    assert np.array_equal(fwd(eng, x, [500.0] * 4), ref_a)   # still cached
+    # fill every slot and go past the end: later timesteps are simply recomputed
+    for k in range(140):
+        fwd(eng, x, [float(k)] * 4)
+    assert np.array_equal(fwd(eng, x, [3.0] * 4), fwd(plain, x, [3.0] * 4))      # cached slot
+    assert np.array_equal(fwd(eng, x, [139.0] * 4), fwd(plain, x, [139.0] * 4))  # past the end
+    assert np.array_equal(fwd(eng, x2, [500.0] * 4), ref_b)
